@@ -1,0 +1,103 @@
+// Host side of the tcgen05 GEMM: plan construction (TMA descriptors, tile choice) and launch.
+#pragma once
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace thmr {
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmParams p;
+  int bn;
+  int grid;
+};
+
+struct GemmDesc {
+  const __half* A; int lda; long long a_rows;  // a_rows: rows addressable through the A descriptor
+  const __half* B; int ldb;
+  int M, N, K;
+  const float* bias = nullptr;
+  const float* resid = nullptr; int ldr = 0; int resid_mod = 0;
+  int act = kActNone;
+  float* out32 = nullptr; int ld32 = 0;
+  __half* out16 = nullptr; int ld16 = 0;
+  // implicit conv1d (taps > 1): K = taps * cin, tap t reads A rows (m + tap_row0 + t*tap_stride), cols [0,cin)
+  int taps = 1; int cin = 0; int tap_row0 = 0; int tap_stride = 0;
+  int seq_pitch = 0, seq_lo = 0, seq_hi = 0;
+  int force_bn = 0;
+};
+
+inline int pick_bn(int M, int N, int force) {
+  if (force) return force;
+  const int sms = num_sms();
+  const int tm = (M + kGemmBM - 1) / kGemmBM;
+  int best = 256;
+  long best_cost = -1;
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long tiles = static_cast<long>(tm) * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    // MMA time per tile scales with BN (M fixed at 128); + fixed per-tile cost; narrow tiles
+    // are smem-bandwidth bound (A re-read per column block), so weight them up.
+    const long per_tile = bn + 24 + (bn < 128 ? (128 - bn) / 2 : 0);
+    const long cost = waves * per_tile;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
+  THMR_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: bad shape %dx%dx%d", d.M, d.N, d.K);
+  THMR_CHECK(d.out32 || d.out16, "gemm: no output");
+  const int bn = pick_bn(d.M, d.N, d.force_bn);
+  THMR_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad block_n %d", bn);
+  GemmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.out32 = d.out32; p.ld32 = d.ld32; p.out16 = d.out16; p.ld16 = d.ld16;
+  p.bias = d.bias; p.resid = d.resid; p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.act = d.act;
+  p.seq_pitch = d.seq_pitch; p.seq_lo = d.seq_lo; p.seq_hi = d.seq_hi;
+  const int num_kb = (d.K + kGemmBK - 1) / kGemmBK;
+  uint64_t a_cols = d.K;
+  if (d.taps > 1) {
+    THMR_CHECK(d.cin % kGemmBK == 0 && d.K == d.taps * d.cin, "gemm conv: cin %d taps %d K %d", d.cin, d.taps, d.K);
+    p.kblocks_per_tap = d.cin / kGemmBK;
+    p.tap_row0 = d.tap_row0; p.tap_stride = d.tap_stride;
+    a_cols = d.cin;
+  } else {
+    p.kblocks_per_tap = num_kb;
+  }
+  THMR_TRY(make_tmap_2d_f16(&plan->tmA, d.A, d.a_rows, a_cols, d.lda, kGemmBM, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, bn, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  plan->bn = bn;
+  const long tiles = static_cast<long>((d.M + kGemmBM - 1) / kGemmBM) * ((d.N + bn - 1) / bn);
+  plan->grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  return THMR_OK;
+}
+
+template <int BN, int STAGES>
+inline int gemm_launch_t(const GemmPlan& plan, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    THMR_CUDA(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   S::kTotal));
+    configured = true;
+  }
+  gemm_f16_tn_kernel<BN, STAGES><<<plan.grid, kGemmThreads, S::kTotal, stream>>>(plan.tmA, plan.tmB, plan.p);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.bn) {
+    case 256: return gemm_launch_t<256, 4>(plan, stream);
+    case 128: return gemm_launch_t<128, 6>(plan, stream);
+    case 64: return gemm_launch_t<64, 8>(plan, stream);
+    case 32: return gemm_launch_t<32, 8>(plan, stream);
+  }
+  return fail(THMR_ERR_INVALID, "gemm: unsupported block_n %d", plan.bn);
+}
+
+}  // namespace thmr

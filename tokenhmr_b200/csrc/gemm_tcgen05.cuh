@@ -1,0 +1,267 @@
+// Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] * B[N,K]^T)
+//   A (activations) and B (nn.Linear / conv weight, stored [out, in]) are both K-major fp16,
+//   accumulation is fp32 in TMEM.
+//
+//   warp 0   : TMA producer (one thread)       global -> 128B-swizzled smem ring
+//   warp 1   : MMA issuer   (one thread)       tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 2   : TMEM allocator / deallocator
+//   warps 4+ : epilogue                         tcgen05.ld -> bias / residual / activation -> global
+//
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+// The same kernel runs the implicit-GEMM Conv1d (k=3, dilated) of the pose-token decoder:
+// k-blocks are grouped in "taps", each tap reads the A rows shifted by a row offset
+// (TMA zero-fills rows that fall outside the tensor).
+#pragma once
+#include "ptx.cuh"
+
+namespace thmr {
+
+enum : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  float* out32;   // acc + bias + resid, fp32 (nullable)
+  int ld32;
+  __half* out16;  // act(acc + bias + resid) rounded to fp16 (nullable)
+  int ld16;
+  const float* bias;   // [N] (nullable)
+  const float* resid;  // fp32 [*, N] (nullable); may alias out32 (same element, same thread)
+  int ldr;
+  int resid_mod;  // > 0: residual row = row % resid_mod (position-embedding table)
+  int act;
+  // implicit conv: tap t = kb / kblocks_per_tap reads A rows (m + tap_row0 + t * tap_stride)
+  int kblocks_per_tap;
+  int tap_row0, tap_stride;
+  // padded sequences: rows with (row % seq_pitch) outside [seq_lo, seq_hi) are stored as zero
+  int seq_pitch, seq_lo, seq_hi;
+};
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 256;  // 4 control warps + 4 epilogue warps
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;
+  static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kBarOffset = STAGES * kStageBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kGemmBM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          const int tap = kb / p.kblocks_per_tap;
+          const int kk = kb - tap * p.kblocks_per_tap;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kk * kGemmBK, m0 + p.tap_row0 + tap * p.tap_stride);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_f16(kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec16 = p.out16 && (p.ld16 % 8 == 0);
+    const bool vec32 = (!p.out32 || p.ld32 % 4 == 0) && (!p.resid || p.ldr % 4 == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * kGemmBM;
+      const int n0 = (tile % tiles_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      bool row_zero = false;
+      if (p.seq_pitch > 0) {
+        const int r = row % p.seq_pitch;
+        row_zero = (r < p.seq_lo) || (r >= p.seq_hi);
+      }
+      const float* rrow = nullptr;
+      if (p.resid) rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldr;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < p.N) {
+          const bool full = (col0 + 32 <= p.N);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (rrow) {
+            if (full && vec32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rrow + col0 + j);
+                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) f[j] += rrow[col0 + j];
+            }
+          }
+          if (row_zero) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          if (p.out32) {
+            float* o = p.out32 + static_cast<size_t>(row) * p.ld32 + col0;
+            if (full && vec32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = f[j];
+            }
+          }
+          if (p.out16) {
+            if (p.act == kActGelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == kActRelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            __half* o = p.out16 + static_cast<size_t>(row) * p.ld16 + col0;
+            if (full && vec16) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
+                __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
+                __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace thmr
