@@ -1,5 +1,5 @@
 /*
- * tokenhmr_b200 — C ABI of the B200-native TokenHMR inference engine.
+ * tokenhmr_b200 — C ABI of the B200-native TokenHMR inference engine (libtokenhmr_b200.so).
  *
  * The reference (saidwivedi/TokenHMR @ 198645f) has no FFI layer: its seam is the Python method
  * TokenHMR.forward(batch) (tokenhmr/lib/models/tokenhmr.py:330-338 -> forward_step :135-188) and the
@@ -7,14 +7,18 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
- *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - functions return THMR_OK (0) or a negative thmr_status; thmr_last_error() holds the message
  *     (thread-local); nothing throws across this boundary;
- *   - the caller owns every buffer it passes (inputs, outputs, workspace); the engine owns only the
- *     repacked weights it creates in thmr_engine_create;
- *   - calls on one engine must be serialised by the caller; kernels are stream-ordered and
- *     CUDA-graph capturable (no host synchronisation inside thmr_engine_forward);
- *   - "f16" buffers hold IEEE binary16 (__half).
+ *   - the caller owns every buffer it passes (inputs, outputs, workspace, weights); weights must outlive
+ *     the engine; the engine owns only the plans (TMA descriptors) and the repacked SMPL model;
+ *   - calls on one engine must be serialised by the caller; all work is stream-ordered, there is no host
+ *     synchronisation inside thmr_engine_forward, and it is CUDA-graph capturable after one eager call;
+ *   - "f16" = IEEE binary16 (__half), row-major, innermost dimension contiguous.
+ *
+ * Numeric contract: every Linear / Conv / attention product rounds its two operands to f16 and
+ * accumulates in fp32 on the tcgen05 tensor cores; LayerNorm, softmax, GELU, residual streams, 6D->rotation,
+ * SMPL skinning and projection are fp32.
  */
 #ifndef TOKENHMR_B200_H_
 #define TOKENHMR_B200_H_
@@ -34,25 +38,201 @@ typedef enum thmr_status {
   THMR_ERR_NOMEM = -4
 } thmr_status;
 
-/* ABI version (bumped on any signature change) and last error message of the calling thread. */
 int thmr_abi_version(void);
 const char* thmr_last_error(void);
 /* Reads and clears the device-side pipeline-timeout flag (synchronises the device). */
 int thmr_check_device_flags(void);
 
-/* ------------------------------------------------------------------------------------------------
- * Standalone operators (each is also a stage of thmr_engine_forward)
- * ---------------------------------------------------------------------------------------------- */
+/* ================================================================================================
+ * Stand-alone operators (each is also a stage of thmr_engine_forward)
+ * ============================================================================================== */
 
 enum { THMR_ACT_NONE = 0, THMR_ACT_GELU = 1, THMR_ACT_RELU = 2 };
 
-/* nn.Linear as one tcgen05 GEMM:  y = x @ W^T (+ bias) (+ resid)   [vit.py:82-86,112,123; every F.linear on the path]
- *   A [M,K] f16 row-major (lda), B = weight [N,K] f16 row-major (ldb), fp32 accumulate.
- *   out32 (nullable) receives acc+bias+resid in fp32; out16 (nullable) receives act(acc+bias+resid) in f16.
- *   resid (nullable, fp32 [M,N], pitch ldr) may alias out32.  block_n: 0 = auto, else 32/64/128/256. */
+/* nn.Linear as one tcgen05 GEMM:  y = x @ W^T (+ bias) (+ resid)      [vit.py:82-86,112,123; any F.linear]
+ *   A [M,K] f16 (pitch lda), B = weight [N,K] f16 (pitch ldb), fp32 accumulate in TMEM.
+ *   out32 (nullable) <- acc+bias+resid (fp32);  out16 (nullable) <- act(acc+bias+resid) (f16).
+ *   resid (nullable, fp32, pitch ldr) may alias out32.  block_n: 0 = auto, else 32/64/128/256. */
 int thmr_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                   const float* resid, int ldr, int act, float* out32, int ld32, void* out16, int ld16, int block_n,
                   void* stream);
+
+/* nn.Conv1d(Cin, Cout, 3, stride 1, padding = dilation, dilation) on channels-last zero-padded sequences
+ * [resnet.py:47, vanilla_pose_vqvae.py:135-152] as an implicit tcgen05 GEMM.
+ *   x   f16 [B, L + 2*pad, Cin]  (pad rows must be zero, pad >= dilation),  w f16 [Cout, 3*Cin] with
+ *   k = tap*Cin + c (tap-major repack of the reference's [Cout, Cin, 3]),  bias fp32 [Cout].
+ *   Outputs use the same padded layout (pad rows written as zero). */
+int thmr_conv1d_k3_f16(const void* x, int B, int L, int pad, int Cin, const void* w, int Cout, const float* bias,
+                       int dilation, int act, float* out32, void* out16, void* stream);
+
+/* nn.LayerNorm over the last dim [vit.py:136,144,252; pose_transformer.py:29; modules.py:17,50,52].
+ *   x fp32 [R,C] -> y16 (f16, nullable) and/or y32 (fp32, nullable); optional fused ReLU (modules.py:15-19). */
+int thmr_layernorm(const float* x, const float* gamma, const float* beta, int R, int C, float eps, int relu,
+                   void* y16, float* y32, void* stream);
+
+/* ViT attention core  softmax(q k^T * 80^-0.5) v  for all heads [vit.py:113-122].
+ *   qkv f16 [B*192, 3*H*80] exactly as produced by Attention.qkv (q heads, then k, then v);
+ *   out f16 [B*192, H*80];  dbg_scores (nullable) fp32 [B*H,192,192] receives the raw q.k^T (tests). */
+int thmr_vit_attention(const void* qkv, int B, int heads, void* out, float* dbg_scores, void* stream);
+
+/* QuantizeEMAReset.quantize  [tokenization/models/quantize_cnn.py:80-86]:
+ *   idx[q] = argmin_k ( sum x_q^2 - 2 x_q . c_k + sum c_k^2 ), first minimum, int64.
+ *   x fp32 [Q,D], codebook fp32 [K,D] (D % 64 == 0).  workspace: thmr_vq_workspace_bytes(Q,K,D) bytes. */
+size_t thmr_vq_workspace_bytes(int64_t Q, int K, int D);
+int thmr_vq_argmin(const float* x, int64_t Q, const float* codebook, int K, int D, int64_t* idx, void* workspace,
+                   void* stream);
+/* QuantizeEMAReset.dequantize (F.embedding) [quantize_cnn.py:88-90]: out[q] = codebook[idx[q]]. */
+int thmr_vq_dequantize(const int64_t* idx, int64_t Q, const float* codebook, int D, float* out, void* stream);
+/* QuantizeEMAReset.dequantize_logits [quantize_cnn.py:92-93]: out = logits @ codebook.
+ *   logits f16 [Q,K], codebook_t f16 [D,K] (transposed codebook), out fp32 [Q,D]. */
+int thmr_vq_dequant_logits(const void* logits16, int64_t Q, int K, const void* codebook_t16, int D, float* out,
+                           void* stream);
+
+/* rot6d_to_rotmat [tokenhmr/lib/utils/geometry.py:64-84]: x fp32 [N,6] -> rot fp32 [N,3,3]. */
+int thmr_rot6d_to_rotmat(const float* x6, int64_t N, float* rot, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SMPL body model (smplx==0.1.28 SMPLLayer / lbs, wrapped by tokenhmr/lib/models/smpl_wrapper.py:10-41)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thmr_smpl thmr_smpl;
+
+typedef struct thmr_smpl_desc {
+  int num_verts;                 /* 6890 */
+  int num_betas;                 /* <= 10 */
+  const float* v_template;       /* [V,3] */
+  const float* shapedirs;        /* [V,3,num_betas] */
+  const float* posedirs;         /* [207, 3V] */
+  const float* J_regressor;      /* [24,V] */
+  const float* lbs_weights;      /* [V,24] */
+  const int32_t* parents_host;   /* [24], parents[0] = -1 */
+  const float* joint_regressor_extra; /* [n_extra, V] (nullable) */
+  int n_extra;                   /* 19 */
+  const int32_t* extra_vertex_ids_host; /* [21] VertexJointSelector vertex ids */
+  const int32_t* joint_map_host; /* [25] smpl_to_openpose (smpl_wrapper.py:19-20) */
+} thmr_smpl_desc;
+
+/* Copies / repacks the model into engine-owned device memory (the descriptor's buffers may be freed after). */
+int thmr_smpl_create(const thmr_smpl_desc* desc, thmr_smpl** out);
+void thmr_smpl_destroy(thmr_smpl* m);
+size_t thmr_smpl_workspace_bytes(const thmr_smpl* m, int batch);
+
+/* smplx.lbs.lbs(betas, pose, ..., pose2rot):  pose fp32 [B,24,3] axis-angle (pose2rot=1) or [B,24,3,3]
+ * (pose2rot=0); betas fp32 [B,num_betas]  ->  verts fp32 [B,V,3], joints fp32 [B,24,3] (J_transformed). */
+int thmr_lbs(const thmr_smpl* m, const float* pose, int pose2rot, const float* betas, int B, float* verts,
+             float* joints, void* workspace, void* stream);
+
+/* SMPL wrapper forward [smpl_wrapper.py:27-41 on top of SMPLLayer.forward]: rotation matrices in,
+ * verts fp32 [B,V,3] and joints fp32 [B,25+n_extra,3] (OpenPose-mapped + regressed extra joints) out.
+ * If pred_cam (fp32 [B,3], nullable) is given the tail of forward_step is fused in (tokenhmr.py:165-187):
+ * cam_t [B,3], focal_out [B,2], kp2d [B,25+n_extra,2]. */
+int thmr_smpl_forward(const thmr_smpl* m, const float* rotmats /* [B,24,3,3] */, const float* betas, int B,
+                      float* verts, float* joints, const float* pred_cam, float focal_length, float image_size,
+                      float* cam_t, float* focal_out, float* kp2d, void* workspace, void* stream);
+
+/* ================================================================================================
+ * Engine: TokenHMR.forward(batch)  [tokenhmr.py:330-338 -> 135-188]
+ * ============================================================================================== */
+typedef struct thmr_engine thmr_engine;
+
+typedef struct thmr_config {
+  int image_size, crop_w, patch, patch_pad;           /* 256, 192, 16, 2 */
+  int vit_dim, vit_depth, vit_heads, vit_mlp_ratio;   /* 1280, 32, 16, 4  (head_dim must be 80, 192 tokens) */
+  float vit_ln_eps;                                   /* 1e-6 */
+  int dec_dim, dec_depth, dec_heads, dec_dim_head, dec_mlp_dim; /* 1024, 6, 8, 64, 1024 */
+  float ln_eps;                                       /* 1e-5 */
+  int token_num, token_class_num, cls_hidden, cls_hidden_inter, cls_token_inter, cls_blocks; /* 160,2048,64,256,64,4 */
+  int code_dim, tok_width, tok_depth, tok_dilation_rate, tok_joints; /* 256, 512, 2, 3, 21 */
+  int n_upsample;                                     /* 4 */
+  int upsample_sizes[8];                              /* 125, 90, 55, 21 */
+  float focal_length;                                 /* 5000 */
+} thmr_config;
+
+/* Weight pointers, packed by the host loader (tokenhmr_b200/weights.py) from the reference state_dicts.
+ * "w" matrices are f16 [out,in] (nn.Linear layout); vectors are fp32. */
+typedef struct thmr_vit_block {
+  const float *ln1_g, *ln1_b;
+  const void* qkv_w; const float* qkv_b;      /* [3D,D] */
+  const void* proj_w; const float* proj_b;    /* [D,D] */
+  const float *ln2_g, *ln2_b;
+  const void* fc1_w; const float* fc1_b;      /* [4D,D] */
+  const void* fc2_w; const float* fc2_b;      /* [D,4D] */
+} thmr_vit_block;
+
+typedef struct thmr_dec_layer {
+  const float *ln0_g, *ln0_b;
+  const void* sa_v_w;                          /* V third of to_qkv: [inner, E] */
+  const void* sa_out_w; const float* sa_out_b; /* [E, inner] */
+  const float *ln1_g, *ln1_b;
+  const void* ca_q_w;                          /* [inner, E] */
+  const void* ca_out_w; const float* ca_out_b; /* [E, inner] */
+  const float *ln2_g, *ln2_b;
+  const void* ff1_w; const float* ff1_b;       /* [mlp, E] */
+  const void* ff2_w; const float* ff2_b;       /* [E, mlp] */
+} thmr_dec_layer;
+
+typedef struct thmr_mixer_block {
+  const float *ln1_g, *ln1_b;
+  const void* tok1_w; const float* tok1_b;     /* [token_inter, T] */
+  const void* tok2_w; const float* tok2_b;     /* [T, token_inter] */
+  const float *ln2_g, *ln2_b;
+  const void* ch1_w; const float* ch1_b;       /* [hidden_inter, H] */
+  const void* ch2_w; const float* ch2_b;       /* [H, hidden_inter] */
+} thmr_mixer_block;
+
+typedef struct thmr_conv { const void* w; const float* b; } thmr_conv; /* w f16 [Cout, 3*Cin] tap-major (or [Cout,Cin]) */
+
+typedef struct thmr_weights {
+  /* ViT */
+  const void* patch_w; const float* patch_b;   /* [D, 3*P*P] */
+  const float* pos;                            /* [192, D] = pos_embed[1:] + pos_embed[0] */
+  const thmr_vit_block* blocks_host;           /* host array [vit_depth] */
+  const float *last_g, *last_b;
+  /* decoder */
+  const float* token0;                         /* [E] = to_token_embedding.bias + pos_embedding */
+  const void* kv_w;                            /* [dec_depth * 2*inner, D]: to_kv of all layers stacked */
+  const thmr_dec_layer* dec_host;              /* host array [dec_depth] */
+  const void* readout_w; const float* readout_b; /* [32, E]: grot(6) hands(12) shape(10) cam(3) + 1 zero row */
+  const float *init_pose, *init_betas, *init_cam; /* [144], [10], [3] */
+  /* token classifier */
+  const void* mt_w; const float* mt_b; const float *mt_ln_g, *mt_ln_b; /* Linear E -> T*H, LN(T*H) */
+  const thmr_mixer_block* mixer_host;          /* host array [cls_blocks] */
+  const void* mn_w; const float* mn_b; const float *mn_ln_g, *mn_ln_b; /* Linear H->H, LN(H) */
+  const void* cls_w; const float* cls_b;       /* [classes, H] */
+  /* tokenizer */
+  const void* codebook_t;                      /* f16 [code_dim, nb_code] */
+  thmr_conv conv_in;                           /* code_dim -> W */
+  thmr_conv conv_up[8];                        /* after each Upsample */
+  thmr_conv res_conv1[8], res_conv2[8];        /* Resnet1D blocks in stored order (dilation rate^(depth-1) ... 1) */
+  thmr_conv conv_post, conv_out;               /* W -> W, W -> 6 */
+} thmr_weights;
+
+typedef struct thmr_outputs {                  /* all fp32, caller-allocated; any pointer may be NULL */
+  float* cls_logits_softmax;  /* [B,160,2048] */
+  float* pred_cam;            /* [B,3] */
+  float* rotmats;             /* [B,24,3,3]: global_orient = [:, :1], body_pose = [:, 1:] */
+  float* betas;               /* [B,10] */
+  float* pred_cam_t;          /* [B,3] */
+  float* focal_length;        /* [B,2] */
+  float* pred_keypoints_3d;   /* [B,44,3] */
+  float* pred_vertices;       /* [B,V,3] */
+  float* pred_keypoints_2d;   /* [B,44,2] */
+  /* optional taps for stage-level parity tests */
+  float* vit_tokens;          /* [B,192,D] backbone output (token-major) */
+  float* token_out;           /* [B,E] decoder output */
+  float* pose6d;              /* [B,144] */
+} thmr_outputs;
+
+int thmr_engine_create(const thmr_config* cfg, const thmr_weights* w, const thmr_smpl* smpl, thmr_engine** out);
+void thmr_engine_destroy(thmr_engine* e);
+size_t thmr_engine_workspace_bytes(const thmr_engine* e, int max_batch);
+/* img fp32 [B,3,image_size,image_size] (batch['img']).  `workspace` must hold
+ * thmr_engine_workspace_bytes(e, B) bytes, 1024-byte aligned. */
+int thmr_engine_forward(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
+                        void* stream);
+/* Number of kernels one forward launches (for bench.py's gpu_launches). */
+int thmr_engine_num_launches(const thmr_engine* e);
+/* Backbone only: ViT.forward [vit.py:341-343]: img -> tokens fp32 [B,192,D] (token-major). */
+int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,109 @@
+"""Generate tests/golden/*.npz by running the LIVE reference modules (oracle/ref_import.py) on seeded
+synthetic weights and inputs.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden            # tiny (depth-2) + stage goldens, ~10 s
+    python -m oracle.make_golden --release  # also the full ViT-H depth-32 forward (B=2), ~1 min, 2.6 GB RAM
+
+The weights are not stored: tests regenerate them from the same seeds (tokenhmr_b200/synth.py).  TEST
+INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from tokenhmr_b200 import synth
+from tokenhmr_b200.config import release_config, tiny_config
+
+from . import ref_import, smpl_oracle
+
+GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
+W_SEED, SMPL_SEED, IMG_SEED = 1234, 3, 0
+
+
+def forward_golden(ns, cfg, batch: int, name: str) -> None:
+    sd = synth.make_state_dict(cfg, W_SEED)
+    smpl = synth.make_smpl(cfg, SMPL_SEED)
+    img = synth.make_images(batch, cfg, IMG_SEED)
+    bb = ref_import.build_backbone(ns, sd, cfg)
+    head = ref_import.build_head(ns, sd, cfg)
+    out = ref_import.reference_forward(ns, bb, head, smpl, img, cfg)
+    probs = out["cls_logits_softmax"]
+    np.savez_compressed(
+        GOLDEN / name,
+        meta=np.array([W_SEED, SMPL_SEED, IMG_SEED, batch, cfg.vit_depth, cfg.num_verts]),
+        vit_tokens_sub=out["_vit_tokens"][:, ::8].numpy(),          # every 8th token, all channels
+        cls_argmax=probs.argmax(-1).numpy().astype(np.int16),
+        cls_maxprob=probs.max(-1).values.numpy(),
+        cls_probs_sub=probs[:, ::16].numpy().astype(np.float32),     # every 16th token position, all classes
+        pred_cam=out["pred_cam"].numpy(), pred_cam_t=out["pred_cam_t"].numpy(),
+        focal_length=out["focal_length"].numpy(),
+        global_orient=out["pred_smpl_params"]["global_orient"].numpy(),
+        body_pose=out["pred_smpl_params"]["body_pose"].numpy(),
+        betas=out["pred_smpl_params"]["betas"].numpy(),
+        pred_keypoints_3d=out["pred_keypoints_3d"].numpy(), pred_vertices=out["pred_vertices"].numpy(),
+        pred_keypoints_2d=out["pred_keypoints_2d"].numpy())
+    print("wrote", name)
+
+
+def stage_goldens(ns) -> None:
+    cfg = release_config()
+    g = torch.Generator().manual_seed(7)
+    # --- QuantizeEMAReset.quantize / dequantize / dequantize_logits (quantize_cnn.py:80-93)
+    qz = ns.quantize_cnn.QuantizeEMAReset(cfg.nb_code, cfg.code_dim)
+    codebook = torch.randn(cfg.nb_code, cfg.code_dim, generator=torch.Generator().manual_seed(1))
+    qz.codebook = codebook
+    x_rand = torch.randn(4096, cfg.code_dim, generator=torch.Generator().manual_seed(2))
+    pick = torch.randint(0, cfg.nb_code, (4096,), generator=g)
+    x_near = codebook[pick] + 0.05 * torch.randn(4096, cfg.code_dim, generator=g)
+    with torch.no_grad():
+        idx_rand = qz.quantize(x_rand)
+        idx_near = qz.quantize(x_near)
+        k_w = codebook.t()
+        d = (x_rand ** 2).sum(-1, keepdim=True) - 2 * x_rand @ k_w + (k_w ** 2).sum(0, keepdim=True)
+        top2 = d.topk(2, dim=-1, largest=False).values
+        logits = torch.softmax(4 * torch.randn(64, cfg.nb_code, generator=g), -1)
+        deq = qz.dequantize_logits(logits)
+    np.savez_compressed(GOLDEN / "vq_quantize.npz", idx_rand=idx_rand.numpy(), idx_near=idx_near.numpy(),
+                        pick=pick.numpy(), gap_rand=(top2[:, 1] - top2[:, 0]).numpy(),
+                        logits=logits.numpy(), dequant_logits=deq.numpy())
+    # --- rot6d_to_rotmat + perspective_projection (geometry.py:64-124)
+    x6 = torch.randn(256, 6, generator=g)
+    pts = torch.randn(4, 44, 3, generator=g) + torch.tensor([0., 0., 20.])
+    tr = torch.randn(4, 3, generator=g)
+    fl = torch.full((4, 2), 5000. / 256)
+    with torch.no_grad():
+        R = ns.geometry.rot6d_to_rotmat(x6)
+        proj = ns.geometry.perspective_projection(pts, translation=tr, focal_length=fl)
+    np.savez_compressed(GOLDEN / "geometry.npz", x6=x6.numpy(), rotmat=R.numpy(), pts=pts.numpy(), tr=tr.numpy(),
+                        fl=fl.numpy(), proj=proj.numpy())
+    # --- SMPL lbs restatement (UNPINNED: produced by oracle/smpl_oracle.py in float64, stored as regression
+    #     fixture so later changes to the restatement are visible)
+    smpl = synth.make_smpl(cfg, SMPL_SEED)
+    aa = 0.3 * torch.randn(8, 24, 3, generator=g)
+    betas = torch.randn(8, 10, generator=g)
+    R = smpl_oracle.batch_rodrigues(aa.double().view(-1, 3)).view(8, 24, 3, 3)
+    v, j = smpl_oracle.smpl_forward(smpl, R[:, :1], R[:, 1:], betas.double(), dtype=torch.float64)
+    np.savez_compressed(GOLDEN / "smpl_lbs_f64.npz", aa=aa.numpy(), betas=betas.numpy(),
+                        verts=v.numpy().astype(np.float32), joints=j.numpy().astype(np.float32))
+    print("wrote stage goldens")
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--release", action="store_true")
+    args = ap.parse_args()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    ns = ref_import.load_modules()
+    stage_goldens(ns)
+    forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
+    if args.release:
+        forward_golden(ns, release_config(), 2, "forward_release_d32.npz")
+
+
+if __name__ == "__main__":
+    main()

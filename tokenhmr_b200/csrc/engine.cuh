@@ -1,0 +1,408 @@
+// Engine: orchestrates TokenHMR.forward (tokenhmr.py:135-188) as a fixed list of stream-ordered launches
+// over a caller-provided workspace.  Plans (TMA descriptors, tile shapes) are built once per
+// (workspace, batch) and replayed; nothing here synchronises the host, so the whole forward can be
+// captured in a CUDA graph by the caller.
+#pragma once
+#include <functional>
+#include <vector>
+
+#include "attention_tcgen05.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_host.cuh"
+#include "head_kernels.cuh"
+#include "smpl_lbs.cuh"
+#include "vq.cuh"
+
+struct thmr_smpl {
+  thmr::SmplModel m;
+  int* parents_dev = nullptr;
+};
+
+namespace thmr {
+
+struct RunCtx {
+  const float* img;
+  thmr_outputs out;
+  float* vit_tokens_only;  // thmr_engine_vit_forward target
+};
+
+using StepFn = std::function<int(const RunCtx&, cudaStream_t)>;
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// ---- SMPL stage (shared by thmr_lbs / thmr_smpl_forward / the engine) -----------------------------------
+struct SmplWs {
+  float* A;        // [B,24,12]
+  float* Jposed;   // [B,24,3]
+  __half* pf16;    // [B,624]
+  float* offsets;  // [B,3V]
+};
+inline void smpl_carve(Bump& bp, const SmplModel& m, int B, SmplWs* ws) {
+  ws->A = bp.take<float>(static_cast<size_t>(B) * kSmplJ * 12);
+  ws->Jposed = bp.take<float>(static_cast<size_t>(B) * kSmplJ * 3);
+  ws->pf16 = bp.take<__half>(static_cast<size_t>(B) * 3 * kSmplPFPad);
+  ws->offsets = bp.take<float>(static_cast<size_t>(B) * 3 * m.V);
+}
+
+// verts: fp32 [B,V,3];  lbs_joints (nullable): [B,24,3];  joints44 (nullable): [B,25+n_extra,3]
+inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const float* betas, int B, float* verts,
+                    float* lbs_joints, float* joints44, const float* pred_cam, float focal, float image_size,
+                    float* cam_t, float* focal_out, float* kp2d, const SmplWs& ws, const GemmPlan* blend_plan,
+                    cudaStream_t st) {
+  const SmplModel& m = sm->m;
+  smpl_pose_kernel<<<B, 32, 0, st>>>(pose, pose2rot, betas, m.J_template, m.J_shapedirs, m.nb, sm->parents_dev, ws.A,
+                                     lbs_joints ? lbs_joints : ws.Jposed, ws.pf16, B);
+  THMR_CUDA(cudaGetLastError());
+  GemmPlan local;
+  if (!blend_plan) {
+    GemmDesc d;
+    d.A = ws.pf16; d.lda = 3 * kSmplPFPad; d.a_rows = B;
+    d.B = m.posedirsT; d.ldb = 3 * kSmplPFPad;
+    d.M = B; d.N = 3 * m.V; d.K = 3 * kSmplPFPad;
+    d.out32 = ws.offsets; d.ld32 = 3 * m.V;
+    d.alpha = 1.0f / (kSplitScale * kSplitScale);
+    THMR_TRY(gemm_make_plan(d, &local));
+    blend_plan = &local;
+  }
+  THMR_TRY(gemm_launch(*blend_plan, st));
+  dim3 grid((m.V + kSkinThreads - 1) / kSkinThreads, (B + kSkinPoses - 1) / kSkinPoses);
+  smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.v_template, m.shapedirs, m.nb, m.w_idx, m.w_val, m.ell, betas, ws.A,
+                                                  ws.offsets, verts, static_cast<long>(m.V) * 3, m.V, B);
+  THMR_CUDA(cudaGetLastError());
+  if (joints44) {
+    smpl_joints_kernel<<<B, 64, 0, st>>>(lbs_joints ? lbs_joints : ws.Jposed, verts, static_cast<long>(m.V) * 3,
+                                         m.joint_map, m.extra_vid, m.jx_ptr, m.jx_idx, m.jx_val, m.n_extra, joints44,
+                                         pred_cam, focal, image_size, cam_t, focal_out, kp2d);
+    THMR_CUDA(cudaGetLastError());
+  }
+  return THMR_OK;
+}
+
+}  // namespace thmr
+
+struct thmr_engine {
+  thmr_config cfg;
+  thmr_weights w;
+  std::vector<thmr_vit_block> blocks;
+  std::vector<thmr_dec_layer> dec;
+  std::vector<thmr_mixer_block> mixer;
+  const thmr_smpl* smpl = nullptr;
+  // plan cache
+  void* ws = nullptr;
+  int B = 0;
+  std::vector<thmr::StepFn> steps;
+  size_t vit_steps = 0;  // steps [0, vit_steps) = backbone
+};
+
+namespace thmr {
+
+constexpr int kTokPad = 3;  // zero rows on both ends of every tokenizer-decoder sequence (max dilation)
+
+inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, int* status, cudaStream_t stream) {
+  const thmr_config& c = e->cfg;
+  const thmr_weights& w = e->w;
+  *status = THMR_OK;
+  Bump bp(workspace);
+  const int T = 192, D = c.vit_dim, M = B * T, H = c.vit_heads;
+  const int E = c.dec_dim, inner = c.dec_heads * c.dec_dim_head, L = c.dec_depth;
+  const int TN = c.token_num, CH = c.cls_hidden, NC = c.token_class_num, W = c.tok_width;
+  const int gh = (c.image_size + 2 * c.patch_pad - c.patch) / c.patch + 1;
+  const int gw = (c.crop_w + 2 * c.patch_pad - c.patch) / c.patch + 1;
+  const int KP = 3 * c.patch * c.patch;
+  const int PAD = kTokPad;
+
+  // ---------------------------------------------------------------- workspace
+  __half* a0 = bp.take<__half>(static_cast<size_t>(M) * KP);
+  float* x = bp.take<float>(static_cast<size_t>(M) * D);
+  __half* xn = bp.take<__half>(static_cast<size_t>(M) * D);
+  __half* qkv = bp.take<__half>(static_cast<size_t>(M) * 3 * D);
+  __half* ao = bp.take<__half>(static_cast<size_t>(M) * D);
+  __half* hbuf = bp.take<__half>(static_cast<size_t>(M) * c.vit_mlp_ratio * D);
+  __half* feat = bp.take<__half>(static_cast<size_t>(M) * D);
+  __half* kv = bp.take<__half>(static_cast<size_t>(M) * L * 2 * inner);
+  float* tok = bp.take<float>(static_cast<size_t>(B) * E);
+  __half* y16 = bp.take<__half>(static_cast<size_t>(B) * E);
+  __half* v16 = bp.take<__half>(static_cast<size_t>(B) * inner);
+  float* q32 = bp.take<float>(static_cast<size_t>(B) * inner);
+  __half* att16 = bp.take<__half>(static_cast<size_t>(B) * inner);
+  __half* hid16 = bp.take<__half>(static_cast<size_t>(B) * c.dec_mlp_dim);
+  float* readout = bp.take<float>(static_cast<size_t>(B) * 32);
+  float* mt32 = bp.take<float>(static_cast<size_t>(B) * TN * CH);
+  float* cx = bp.take<float>(static_cast<size_t>(B) * TN * CH);
+  __half* cx16 = bp.take<__half>(static_cast<size_t>(B) * TN * CH);
+  __half* yT16 = bp.take<__half>(static_cast<size_t>(B) * CH * TN);
+  __half* t1 = bp.take<__half>(static_cast<size_t>(B) * CH * c.cls_token_inter);
+  float* yT32 = bp.take<float>(static_cast<size_t>(B) * CH * TN);
+  float* xy = bp.take<float>(static_cast<size_t>(B) * TN * CH);
+  __half* z16 = bp.take<__half>(static_cast<size_t>(B) * TN * CH);
+  __half* c1 = bp.take<__half>(static_cast<size_t>(B) * TN * c.cls_hidden_inter);
+  float* mn32 = bp.take<float>(static_cast<size_t>(B) * TN * CH);
+  __half* mn16 = bp.take<__half>(static_cast<size_t>(B) * TN * CH);
+  float* logits = bp.take<float>(static_cast<size_t>(B) * TN * NC);
+  float* probs_fallback = bp.take<float>(static_cast<size_t>(B) * TN * NC);
+  const int Lp0 = TN + 2 * PAD;
+  __half* p16 = bp.take<__half>(static_cast<size_t>(B) * Lp0 * NC);
+  __half* d16 = bp.take<__half>(static_cast<size_t>(B) * Lp0 * c.code_dim);
+  __half* bufA = bp.take<__half>(static_cast<size_t>(B) * Lp0 * W);
+  __half* bufB = bp.take<__half>(static_cast<size_t>(B) * Lp0 * W);
+  const int Lj = c.tok_joints, Lpj = Lj + 2 * PAD;
+  float* x32 = bp.take<float>(static_cast<size_t>(B) * Lpj * W);
+  float* out6 = bp.take<float>(static_cast<size_t>(B) * Lpj * 8);
+  float* rot_fb = bp.take<float>(static_cast<size_t>(B) * 24 * 9);
+  float* betas_fb = bp.take<float>(static_cast<size_t>(B) * 16);
+  float* cam_fb = bp.take<float>(static_cast<size_t>(B) * 4);
+  float* camt_fb = bp.take<float>(static_cast<size_t>(B) * 4);
+  float* focal_fb = bp.take<float>(static_cast<size_t>(B) * 2);
+  const int NJ = 25 + e->smpl->m.n_extra;
+  float* kp3_fb = bp.take<float>(static_cast<size_t>(B) * NJ * 3);
+  float* kp2_fb = bp.take<float>(static_cast<size_t>(B) * NJ * 2);
+  float* verts_fb = bp.take<float>(static_cast<size_t>(B) * e->smpl->m.V * 3);
+  SmplWs sws;
+  smpl_carve(bp, e->smpl->m, B, &sws);
+  const size_t total = (bp.off + 1023) & ~size_t(1023);
+  if (!build) return total;
+
+  // ---------------------------------------------------------------- steps
+  std::vector<StepFn>& S = e->steps;
+  S.clear();
+  int err = THMR_OK;
+  auto add_gemm = [&](const GemmDesc& d) {
+    GemmPlan plan;
+    const int s = gemm_make_plan(d, &plan);
+    if (s != THMR_OK) { err = s; return; }
+    S.push_back([plan](const RunCtx&, cudaStream_t st) { return gemm_launch(plan, st); });
+  };
+  auto linear = [&](const __half* A, int lda, int rows, const void* Wt, int N, int K, const float* bias, int act,
+                    float* o32, __half* o16, const float* resid = nullptr) {
+    GemmDesc d;
+    d.A = A; d.lda = lda; d.a_rows = rows;
+    d.B = static_cast<const __half*>(Wt); d.ldb = K;
+    d.M = rows; d.N = N; d.K = K;
+    d.bias = bias; d.act = act; d.resid = resid; d.ldr = N;
+    d.out32 = o32; d.ld32 = N; d.out16 = o16; d.ld16 = N;
+    add_gemm(d);
+  };
+  auto ln = [&](const float* in, const float* g, const float* b, __half* o16, float* o32, int R, int C, float eps,
+                int relu, int out_t) {
+    S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
+      return layernorm_launch(in, g, b, o16, 0, o32, R, C, eps, relu, out_t, st);
+    });
+  };
+
+  // ---- ViT backbone (vit.py:320-343)
+  {
+    const int S_ = c.image_size, x0 = (c.image_size - c.crop_w) / 2, Wc = c.crop_w, P = c.patch, pad = c.patch_pad;
+    S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
+      const long total_t = static_cast<long>(B) * gh * gw * 3 * P;
+      im2col_patch_kernel<<<static_cast<unsigned>((total_t + 255) / 256), 256, 0, st>>>(r.img, a0, B, S_, x0, Wc, P, pad,
+                                                                                       gh, gw);
+      THMR_CUDA(cudaGetLastError());
+      return THMR_OK;
+    });
+    GemmDesc d;
+    d.A = a0; d.lda = KP; d.a_rows = M;
+    d.B = static_cast<const __half*>(w.patch_w); d.ldb = KP;
+    d.M = M; d.N = D; d.K = KP;
+    d.bias = w.patch_b; d.resid = w.pos; d.ldr = D; d.resid_mod = T;
+    d.out32 = x; d.ld32 = D;
+    add_gemm(d);
+  }
+  for (int i = 0; i < c.vit_depth; ++i) {
+    const thmr_vit_block& bw = e->blocks[i];
+    ln(x, bw.ln1_g, bw.ln1_b, xn, nullptr, M, D, c.vit_ln_eps, 0, 0);
+    linear(xn, D, M, bw.qkv_w, 3 * D, D, bw.qkv_b, kActNone, nullptr, qkv);
+    {
+      AttnPlan ap;
+      const int s = attention_make_plan(qkv, 3 * D, B, H, ao, D, nullptr, &ap);
+      if (s != THMR_OK) err = s;
+      S.push_back([ap](const RunCtx&, cudaStream_t st) { return attention_launch(ap, st); });
+    }
+    linear(ao, D, M, bw.proj_w, D, D, bw.proj_b, kActNone, x, nullptr, x);
+    ln(x, bw.ln2_g, bw.ln2_b, xn, nullptr, M, D, c.vit_ln_eps, 0, 0);
+    linear(xn, D, M, bw.fc1_w, c.vit_mlp_ratio * D, D, bw.fc1_b, kActGelu, nullptr, hbuf);
+    linear(hbuf, c.vit_mlp_ratio * D, M, bw.fc2_w, D, c.vit_mlp_ratio * D, bw.fc2_b, kActNone, x, nullptr, x);
+  }
+  {
+    const float* g = w.last_g; const float* b = w.last_b;
+    const float eps = c.vit_ln_eps;
+    S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
+      float* t32 = r.vit_tokens_only ? r.vit_tokens_only : r.out.vit_tokens;
+      return layernorm_launch(x, g, b, feat, 0, t32, M, D, eps, 0, 0, st);
+    });
+  }
+  e->vit_steps = S.size();
+
+  // ---- decoder (pose_transformer.py:191-201,349-357): K/V of all layers in one GEMM
+  linear(feat, D, M, w.kv_w, L * 2 * inner, D, nullptr, kActNone, nullptr, kv);
+  {
+    const float* t0 = w.token0;
+    S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
+      broadcast_row_kernel<<<(B * E + 255) / 256, 256, 0, st>>>(t0, tok, B, E);
+      THMR_CUDA(cudaGetLastError());
+      return THMR_OK;
+    });
+  }
+  for (int l = 0; l < L; ++l) {
+    const thmr_dec_layer& dw = e->dec[l];
+    ln(tok, dw.ln0_g, dw.ln0_b, y16, nullptr, B, E, c.ln_eps, 0, 0);
+    linear(y16, E, B, dw.sa_v_w, inner, E, nullptr, kActNone, nullptr, v16);
+    linear(v16, inner, B, dw.sa_out_w, E, inner, dw.sa_out_b, kActNone, tok, nullptr, tok);
+    ln(tok, dw.ln1_g, dw.ln1_b, y16, nullptr, B, E, c.ln_eps, 0, 0);
+    linear(y16, E, B, dw.ca_q_w, inner, E, nullptr, kActNone, q32, nullptr);
+    {
+      const int ld = L * 2 * inner, koff = l * 2 * inner, voff = koff + inner, heads = c.dec_heads;
+      const float scale = 1.0f / sqrtf(static_cast<float>(c.dec_dim_head));
+      S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
+        dec_cross_attn_kernel<192><<<B, 32 * heads, 0, st>>>(q32, kv, ld, koff, voff, scale, att16, heads);
+        THMR_CUDA(cudaGetLastError());
+        return THMR_OK;
+      });
+    }
+    linear(att16, inner, B, dw.ca_out_w, E, inner, dw.ca_out_b, kActNone, tok, nullptr, tok);
+    ln(tok, dw.ln2_g, dw.ln2_b, y16, nullptr, B, E, c.ln_eps, 0, 0);
+    linear(y16, E, B, dw.ff1_w, c.dec_mlp_dim, E, dw.ff1_b, kActGelu, nullptr, hid16);
+    linear(hid16, c.dec_mlp_dim, B, dw.ff2_w, E, c.dec_mlp_dim, dw.ff2_b, kActNone, tok, nullptr, tok);
+  }
+  // decoder output: optional tap + fp16 operand copy for the read-outs and the classifier
+  S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
+    if (r.out.token_out)
+      THMR_CUDA(cudaMemcpyAsync(r.out.token_out, tok, sizeof(float) * B * E, cudaMemcpyDeviceToDevice, st));
+    const long n4 = static_cast<long>(B) * E / 4;
+    cast_f16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(tok, y16, n4);
+    THMR_CUDA(cudaGetLastError());
+    return THMR_OK;
+  });
+  // read-outs: decpose_grot | decpose_hands | decshape | deccam (token_head.py:99-105) in one GEMM
+  linear(y16, E, B, w.readout_w, 32, E, w.readout_b, kActNone, readout, nullptr);
+
+  // ---- token classifier (token_classifier.py:89-104)
+  linear(y16, E, B, w.mt_w, TN * CH, E, w.mt_b, kActNone, mt32, nullptr);
+  ln(mt32, w.mt_ln_g, w.mt_ln_b, nullptr, cx, B, TN * CH, c.ln_eps, 1, 0);   // FCBlock: LN + ReLU -> x (B*T, H)
+  for (int i = 0; i < c.cls_blocks; ++i) {
+    const thmr_mixer_block& mw = e->mixer[i];
+    // token mixing on the transposed (B*H, T) view (modules.py:56-59)
+    ln(cx, mw.ln1_g, mw.ln1_b, yT16, nullptr, B * TN, CH, c.ln_eps, 0, TN);
+    linear(yT16, TN, B * CH, mw.tok1_w, c.cls_token_inter, TN, mw.tok1_b, kActGelu, nullptr, t1);
+    linear(t1, c.cls_token_inter, B * CH, mw.tok2_w, TN, c.cls_token_inter, mw.tok2_b, kActNone, yT32, nullptr);
+    S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
+      const long n = static_cast<long>(B) * TN * CH;
+      mixer_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(cx, yT32, nullptr, xy, B, TN, CH);
+      THMR_CUDA(cudaGetLastError());
+      return THMR_OK;
+    });
+    // channel mixing (modules.py:60-62): out = (x + y) + MLP_channel(LN2(x + y))
+    ln(xy, mw.ln2_g, mw.ln2_b, z16, nullptr, B * TN, CH, c.ln_eps, 0, 0);
+    linear(z16, CH, B * TN, mw.ch1_w, c.cls_hidden_inter, CH, mw.ch1_b, kActGelu, nullptr, c1);
+    linear(c1, c.cls_hidden_inter, B * TN, mw.ch2_w, CH, c.cls_hidden_inter, mw.ch2_b, kActNone, cx, cx16, xy);
+  }
+  linear(cx16, CH, B * TN, w.mn_w, CH, CH, w.mn_b, kActNone, mn32, nullptr);
+  ln(mn32, w.mn_ln_g, w.mn_ln_b, mn16, nullptr, B * TN, CH, c.ln_eps, 1, 0);
+  linear(mn16, CH, B * TN, w.cls_w, NC, CH, w.cls_b, kActNone, logits, nullptr);
+  S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
+    float* p32 = r.out.cls_logits_softmax ? r.out.cls_logits_softmax : probs_fallback;
+    // pad rows of p16 stay zero: they are cleared once at plan time and never written
+    return softmax_rows_launch(logits, p32, p16, B * TN, NC, TN, Lp0, PAD, st);
+  });
+
+  // ---- tokenizer: soft codebook lookup + Conv1d decoder (vanilla_pose_vqvae.py:294-297, 135-154)
+  {
+    GemmDesc d;   // dequantize_logits on the padded layout (pad rows are zero -> zero output rows)
+    d.A = p16; d.lda = NC; d.a_rows = static_cast<long long>(B) * Lp0;
+    d.B = static_cast<const __half*>(w.codebook_t); d.ldb = NC;
+    d.M = B * Lp0; d.N = c.code_dim; d.K = NC;
+    d.out16 = d16; d.ld16 = c.code_dim;
+    add_gemm(d);
+  }
+  auto conv = [&](const __half* in, int Lcur, int cin, const thmr_conv& cw, int cout, int dil, int taps, int act,
+                  int act32, float* o32, int ld32, __half* o16, const float* resid) {
+    const int Lp = Lcur + 2 * PAD;
+    GemmDesc d;
+    d.A = in; d.lda = cin; d.a_rows = static_cast<long long>(B) * Lp;
+    d.B = static_cast<const __half*>(cw.w); d.ldb = taps * cin;
+    d.M = B * Lp; d.N = cout; d.K = taps * cin;
+    d.bias = cw.b; d.act = act; d.act32 = act32;
+    d.resid = resid; d.ldr = cout;
+    d.out32 = o32; d.ld32 = ld32; d.out16 = o16; d.ld16 = cout;
+    if (taps > 1) { d.taps = taps; d.cin = cin; d.tap_row0 = -dil; d.tap_stride = dil; }
+    d.seq_pitch = Lp; d.seq_lo = PAD; d.seq_hi = PAD + Lcur;
+    add_gemm(d);
+  };
+  int Lcur = TN;
+  conv(d16, Lcur, c.code_dim, w.conv_in, W, 1, 3, kActRelu, 0, nullptr, 0, bufA, nullptr);
+  for (int u = 0; u < c.n_upsample; ++u) {
+    const int Lout = c.upsample_sizes[u], Lin = Lcur;
+    S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
+      const long n = static_cast<long>(B) * (Lout + 2 * PAD) * (W / 8);
+      upsample_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(bufA, bufB, B, Lin, Lout, PAD, W / 8);
+      THMR_CUDA(cudaGetLastError());
+      return THMR_OK;
+    });
+    Lcur = Lout;
+    const bool last = (u == c.n_upsample - 1);
+    conv(bufB, Lcur, W, w.conv_up[u], W, 1, 3, kActRelu, last ? 1 : 0, last ? x32 : nullptr, W, bufA, nullptr);
+  }
+  // Resnet1D (resnet.py:51-82): x = x + conv1x1(relu(conv3_dil(relu(x)))), stored order = dilation descending
+  for (int dd = 0; dd < c.tok_depth; ++dd) {
+    int dil = 1;
+    for (int k = 0; k < c.tok_depth - 1 - dd; ++k) dil *= c.tok_dilation_rate;
+    conv(bufA, Lcur, W, w.res_conv1[dd], W, dil, 3, kActRelu, 0, nullptr, 0, bufB, nullptr);
+    const bool lastb = (dd == c.tok_depth - 1);
+    conv(bufB, Lcur, W, w.res_conv2[dd], W, 1, 1, lastb ? kActNone : kActRelu, 0, x32, W, bufA, x32);
+  }
+  conv(bufA, Lcur, W, w.conv_post, W, 1, 3, kActNone, 0, nullptr, 0, bufB, nullptr);
+  conv(bufB, Lcur, W, w.conv_out, 6, 1, 3, kActNone, 0, out6, 8, nullptr, nullptr);
+
+  // ---- read-out assembly, 6D -> rotation (token_head.py:103-128), SMPL + projection (tokenhmr.py:162-187)
+  {
+    const float* ip = w.init_pose; const float* ib = w.init_betas; const float* ic = w.init_cam;
+    const int nb = e->smpl->m.nb;
+    const thmr_smpl* sm = e->smpl;
+    GemmPlan blend;
+    {
+      GemmDesc d;
+      d.A = sws.pf16; d.lda = 3 * kSmplPFPad; d.a_rows = B;
+      d.B = sm->m.posedirsT; d.ldb = 3 * kSmplPFPad;
+      d.M = B; d.N = 3 * sm->m.V; d.K = 3 * kSmplPFPad;
+      d.out32 = sws.offsets; d.ld32 = 3 * sm->m.V;
+      d.alpha = 1.0f / (kSplitScale * kSplitScale);
+      const int s = gemm_make_plan(d, &blend);
+      if (s != THMR_OK) err = s;
+    }
+    const float focal = c.focal_length, isz = static_cast<float>(c.image_size);
+    S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
+      float* rot = r.out.rotmats ? r.out.rotmats : rot_fb;
+      float* bet = r.out.betas ? r.out.betas : betas_fb;
+      float* cam = r.out.pred_cam ? r.out.pred_cam : cam_fb;
+      head_assemble_kernel<<<(B * 24 + 127) / 128, 128, 0, st>>>(readout, 32, out6, 8, Lpj, PAD, ip, ib, ic, rot, bet, cam,
+                                                                r.out.pose6d, B, nb);
+      THMR_CUDA(cudaGetLastError());
+      float* verts = r.out.pred_vertices ? r.out.pred_vertices : verts_fb;
+      float* kp3 = r.out.pred_keypoints_3d ? r.out.pred_keypoints_3d : kp3_fb;
+      float* kp2 = r.out.pred_keypoints_2d ? r.out.pred_keypoints_2d : kp2_fb;
+      float* camt = r.out.pred_cam_t ? r.out.pred_cam_t : camt_fb;
+      float* foc = r.out.focal_length ? r.out.focal_length : focal_fb;
+      return smpl_run(sm, rot, 0, bet, B, verts, nullptr, kp3, cam, focal, isz, camt, foc, kp2, sws, &blend, st);
+    });
+  }
+  *status = err;
+  // zero the padded fp16 probability buffer once (pad rows are never written afterwards)
+  if (err == THMR_OK) {
+    cudaError_t ce = cudaMemsetAsync(p16, 0, static_cast<size_t>(B) * Lp0 * NC * sizeof(__half), stream);
+    if (ce != cudaSuccess) *status = fail(THMR_ERR_CUDA, "cudaMemsetAsync(p16): %s", cudaGetErrorString(ce));
+  }
+  return total;
+}
+
+}  // namespace thmr

@@ -18,12 +18,14 @@ struct GemmDesc {
   int M, N, K;
   const float* bias = nullptr;
   const float* resid = nullptr; int ldr = 0; int resid_mod = 0;
-  int act = kActNone;
+  int act = kActNone; int act32 = 0;
   float* out32 = nullptr; int ld32 = 0;
   __half* out16 = nullptr; int ld16 = 0;
   // implicit conv1d (taps > 1): K = taps * cin, tap t reads A rows (m + tap_row0 + t*tap_stride), cols [0,cin)
   int taps = 1; int cin = 0; int tap_row0 = 0; int tap_stride = 0;
   int seq_pitch = 0, seq_lo = 0, seq_hi = 0;
+  float alpha = 1.0f;
+  long long* argmin_out = nullptr; const float* row_sq = nullptr; const float* col_sq = nullptr;
   int force_bn = 0;
 };
 
@@ -49,15 +51,16 @@ inline int pick_bn(int M, int N, int force) {
 
 inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: bad shape %dx%dx%d", d.M, d.N, d.K);
-  THMR_CHECK(d.out32 || d.out16, "gemm: no output");
+  THMR_CHECK(d.out32 || d.out16 || d.argmin_out, "gemm: no output");
   const int bn = pick_bn(d.M, d.N, d.force_bn);
   THMR_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad block_n %d", bn);
   GemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.out32 = d.out32; p.ld32 = d.ld32; p.out16 = d.out16; p.ld16 = d.ld16;
-  p.bias = d.bias; p.resid = d.resid; p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.act = d.act;
+  p.bias = d.bias; p.resid = d.resid; p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.act = d.act; p.act32 = d.act32;
   p.seq_pitch = d.seq_pitch; p.seq_lo = d.seq_lo; p.seq_hi = d.seq_hi;
+  p.alpha = d.alpha; p.argmin_out = d.argmin_out; p.row_sq = d.row_sq; p.col_sq = d.col_sq;
   const int num_kb = (d.K + kGemmBK - 1) / kGemmBK;
   uint64_t a_cols = d.K;
   if (d.taps > 1) {
@@ -71,7 +74,8 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_TRY(make_tmap_2d_f16(&plan->tmA, d.A, d.a_rows, a_cols, d.lda, kGemmBM, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, bn, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   plan->bn = bn;
-  const long tiles = static_cast<long>((d.M + kGemmBM - 1) / kGemmBM) * ((d.N + bn - 1) / bn);
+  const long tiles_m = (d.M + kGemmBM - 1) / kGemmBM;
+  const long tiles = d.argmin_out ? tiles_m : tiles_m * ((d.N + bn - 1) / bn);
   plan->grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   return THMR_OK;
 }

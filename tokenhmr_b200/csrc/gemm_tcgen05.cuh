@@ -29,11 +29,42 @@ struct GemmParams {
   int ldr;
   int resid_mod;  // > 0: residual row = row % resid_mod (position-embedding table)
   int act;
+  int act32;  // apply the activation to the fp32 output as well (conv + ReLU feeding a residual)
   // implicit conv: tap t = kb / kblocks_per_tap reads A rows (m + tap_row0 + t * tap_stride)
   int kblocks_per_tap;
   int tap_row0, tap_stride;
   // padded sequences: rows with (row % seq_pitch) outside [seq_lo, seq_hi) are stored as zero
   int seq_pitch, seq_lo, seq_hi;
+  float alpha;  // accumulator scale (split-precision operands are pre-scaled by powers of two)
+  // row-argmin mode (VQ nearest code, quantize_cnn.py:80-86): the CTA walks all column tiles of one row
+  // block and keeps a running first-minimum of  d = (row_sq[row] - 2*alpha*acc) + col_sq[col]
+  long long* argmin_out;   // [M] int64 (nullable = normal GEMM)
+  const float* row_sq;     // [M]
+  const float* col_sq;     // [N]
+};
+
+// Tile order shared by the three warp roles.  Normal mode: tiles round-robin over CTAs, column tile
+// fastest.  Row-argmin mode: row blocks round-robin over CTAs, all column tiles of a row block in sequence.
+struct TileIter {
+  int tiles_m, tiles_n, m_blk, n_blk, tile, num_tiles;
+  bool m_stationary;
+  __device__ TileIter(int tm, int tn, bool ms) : tiles_m(tm), tiles_n(tn), m_stationary(ms) {
+    num_tiles = tm * tn;
+    tile = blockIdx.x;
+    m_blk = blockIdx.x;
+    n_blk = 0;
+  }
+  __device__ bool valid() const { return m_stationary ? (m_blk < tiles_m) : (tile < num_tiles); }
+  __device__ int m0(int bm) const { return (m_stationary ? m_blk : tile / tiles_n) * bm; }
+  __device__ int n0(int bn) const { return (m_stationary ? n_blk : tile % tiles_n) * bn; }
+  __device__ bool last_n() const { return n_blk == tiles_n - 1; }
+  __device__ void next() {
+    if (m_stationary) {
+      if (++n_blk == tiles_n) { n_blk = 0; m_blk += gridDim.x; }
+    } else {
+      tile += gridDim.x;
+    }
+  }
 };
 
 constexpr int kGemmBM = 128;
@@ -72,7 +103,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
   if (warp == 0 && lane == 0) {
@@ -104,9 +134,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * kGemmBM;
-        const int n0 = (tile % tiles_n) * BN;
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+        const int m0 = it.m0(kGemmBM);
+        const int n0 = it.n0(BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
@@ -128,7 +158,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -157,9 +187,11 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     const bool vec16 = p.out16 && (p.ld16 % 8 == 0);
     const bool vec32 = (!p.out32 || p.ld32 % 4 == 0) && (!p.resid || p.ldr % 4 == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * kGemmBM;
-      const int n0 = (tile % tiles_n) * BN;
+    float best = INFINITY;
+    long long best_idx = 0;
+    for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+      const int m0 = it.m0(kGemmBM);
+      const int n0 = it.n0(BN);
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       bool row_zero = false;
@@ -178,11 +210,23 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
+        if (p.argmin_out) {
+          if (row_ok && col0 < p.N) {
+            const float x2 = __ldg(p.row_sq + row);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                // same expression order as the reference: (sum x^2 - 2 x.c) + sum c^2
+                const float d = (x2 - 2.0f * (p.alpha * __uint_as_float(v[j]))) + __ldg(p.col_sq + col0 + j);
+                if (d < best) { best = d; best_idx = col0 + j; }
+              }
+            }
+          }
+        } else if (row_ok && col0 < p.N) {
           const bool full = (col0 + 32 <= p.N);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -205,6 +249,15 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
+          if (p.act32) {
+            if (p.act == kActGelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == kActRelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          }
           if (p.out32) {
             float* o = p.out32 + static_cast<size_t>(row) * p.ld32 + col0;
             if (full && vec32) {
@@ -218,7 +271,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           if (p.out16) {
-            if (p.act == kActGelu) {
+            if (p.act32) {
+            } else if (p.act == kActGelu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
             } else if (p.act == kActRelu) {
@@ -247,6 +301,11 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
         }
+      }
+      if (p.argmin_out && it.last_n()) {
+        if (row_ok) p.argmin_out[row] = best_idx;
+        best = INFINITY;
+        best_idx = 0;
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
       tc_fence_before();

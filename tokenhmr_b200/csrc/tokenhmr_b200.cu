@@ -1,13 +1,39 @@
 // Single translation unit of libtokenhmr_b200.so: device kernels (*.cuh) + the extern "C" ABI
 // declared in include/tokenhmr_b200.h.
+#include <algorithm>
+#include <new>
+
 #include "common.cuh"
-#include "gemm_host.cuh"
+#include "engine.cuh"
 
 using namespace thmr;
 
+namespace {
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(THMR_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  return THMR_OK;
+}
+template <typename T>
+int dev_upload(T** p, const std::vector<T>& h) {
+  THMR_TRY(dev_alloc(p, h.size()));
+  if (!h.empty()) THMR_CUDA(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return THMR_OK;
+}
+template <typename T>
+int dev_clone(T** p, const T* src, size_t n) {
+  THMR_TRY(dev_alloc(p, n));
+  THMR_CUDA(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyDefault));
+  return THMR_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
-int thmr_abi_version(void) { return 1; }
+int thmr_abi_version(void) { return 2; }
 
 const char* thmr_last_error(void) { return last_error_buf(); }
 
@@ -23,6 +49,7 @@ int thmr_check_device_flags(void) {
   return THMR_OK;
 }
 
+// ------------------------------------------------------------------------------------------ GEMM / conv
 int thmr_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                   const float* resid, int ldr, int act, float* out32, int ld32, void* out16, int ld16, int block_n,
                   void* stream) {
@@ -37,6 +64,307 @@ int thmr_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   GemmPlan plan;
   THMR_TRY(gemm_make_plan(d, &plan));
   return gemm_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+int thmr_conv1d_k3_f16(const void* x, int B, int L, int pad, int Cin, const void* w, int Cout, const float* bias,
+                       int dilation, int act, float* out32, void* out16, void* stream) {
+  THMR_CHECK(x && w && B > 0 && L > 0, "conv1d: bad arguments");
+  THMR_CHECK(pad >= dilation && dilation >= 1, "conv1d: pad %d < dilation %d", pad, dilation);
+  const int Lp = L + 2 * pad;
+  GemmDesc d;
+  d.A = static_cast<const __half*>(x); d.lda = Cin; d.a_rows = static_cast<long long>(B) * Lp;
+  d.B = static_cast<const __half*>(w); d.ldb = 3 * Cin;
+  d.M = B * Lp; d.N = Cout; d.K = 3 * Cin;
+  d.bias = bias; d.act = act;
+  d.out32 = out32; d.ld32 = Cout; d.out16 = static_cast<__half*>(out16); d.ld16 = Cout;
+  d.taps = 3; d.cin = Cin; d.tap_row0 = -dilation; d.tap_stride = dilation;
+  d.seq_pitch = Lp; d.seq_lo = pad; d.seq_hi = pad + L;
+  GemmPlan plan;
+  THMR_TRY(gemm_make_plan(d, &plan));
+  return gemm_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+int thmr_layernorm(const float* x, const float* gamma, const float* beta, int R, int C, float eps, int relu,
+                   void* y16, float* y32, void* stream) {
+  THMR_CHECK(x && gamma && beta && (y16 || y32), "layernorm: null argument");
+  return layernorm_launch(x, gamma, beta, static_cast<__half*>(y16), 0, y32, R, C, eps, relu, 0,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int thmr_vit_attention(const void* qkv, int B, int heads, void* out, float* dbg_scores, void* stream) {
+  THMR_CHECK(qkv && out, "attention: null argument");
+  AttnPlan plan;
+  THMR_TRY(attention_make_plan(static_cast<const __half*>(qkv), 3 * heads * kAttHeadDim, B, heads,
+                               static_cast<__half*>(out), heads * kAttHeadDim, dbg_scores, &plan));
+  return attention_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ VQ
+size_t thmr_vq_workspace_bytes(int64_t Q, int K, int D) {
+  Bump bp(nullptr);
+  bp.take<__half>(static_cast<size_t>(Q) * 3 * D);
+  bp.take<__half>(static_cast<size_t>(K) * 3 * D);
+  bp.take<float>(Q);
+  bp.take<float>(K);
+  return (bp.off + 1023) & ~size_t(1023);
+}
+
+int thmr_vq_argmin(const float* x, int64_t Q, const float* codebook, int K, int D, int64_t* idx, void* workspace,
+                   void* stream) {
+  THMR_CHECK(x && codebook && idx && workspace, "vq_argmin: null argument");
+  THMR_CHECK(D % 64 == 0 && Q > 0 && K > 0 && Q < (1ll << 31), "vq_argmin: unsupported shape Q=%lld K=%d D=%d",
+             (long long)Q, K, D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Bump bp(workspace);
+  __half* xs = bp.take<__half>(static_cast<size_t>(Q) * 3 * D);
+  __half* cs = bp.take<__half>(static_cast<size_t>(K) * 3 * D);
+  float* x2 = bp.take<float>(Q);
+  float* c2 = bp.take<float>(K);
+  vq_split_rows_kernel<<<static_cast<unsigned>((Q + 7) / 8), 256, 0, st>>>(x, xs, x2, Q, D, 1);
+  THMR_CUDA(cudaGetLastError());
+  vq_split_rows_kernel<<<static_cast<unsigned>((K + 7) / 8), 256, 0, st>>>(codebook, cs, c2, K, D, 0);
+  THMR_CUDA(cudaGetLastError());
+  GemmDesc d;
+  d.A = xs; d.lda = 3 * D; d.a_rows = Q;
+  d.B = cs; d.ldb = 3 * D;
+  d.M = static_cast<int>(Q); d.N = K; d.K = 3 * D;
+  d.alpha = 1.0f / (kVqScale * kVqScale);
+  d.argmin_out = reinterpret_cast<long long*>(idx); d.row_sq = x2; d.col_sq = c2;
+  d.force_bn = 256;
+  GemmPlan plan;
+  THMR_TRY(gemm_make_plan(d, &plan));
+  return gemm_launch(plan, st);
+}
+
+int thmr_vq_dequantize(const int64_t* idx, int64_t Q, const float* codebook, int D, float* out, void* stream) {
+  THMR_CHECK(idx && codebook && out && D % 4 == 0, "vq_dequantize: bad argument");
+  const long n = Q * (D / 4);
+  vq_gather_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(idx), codebook, out, Q, D / 4);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+int thmr_vq_dequant_logits(const void* logits16, int64_t Q, int K, const void* codebook_t16, int D, float* out,
+                           void* stream) {
+  return thmr_gemm_f16(logits16, K, codebook_t16, K, static_cast<int>(Q), D, K, nullptr, nullptr, 0, THMR_ACT_NONE, out,
+                       D, nullptr, 0, 0, stream);
+}
+
+int thmr_rot6d_to_rotmat(const float* x6, int64_t N, float* rot, void* stream) {
+  THMR_CHECK(x6 && rot, "rot6d: null argument");
+  rot6d_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x6, rot, N);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SMPL
+void thmr_smpl_destroy(thmr_smpl* s) {
+  if (!s) return;
+  SmplModel& m = s->m;
+  cudaFree(m.v_template); cudaFree(m.shapedirs); cudaFree(m.J_template); cudaFree(m.J_shapedirs);
+  cudaFree(m.posedirsT); cudaFree(m.w_idx); cudaFree(m.w_val); cudaFree(m.jx_ptr); cudaFree(m.jx_idx);
+  cudaFree(m.jx_val); cudaFree(m.extra_vid); cudaFree(m.joint_map); cudaFree(s->parents_dev);
+  delete s;
+}
+
+int thmr_smpl_create(const thmr_smpl_desc* d, thmr_smpl** out) {
+  THMR_CHECK(d && out, "smpl_create: null argument");
+  THMR_CHECK(d->num_verts > 0 && d->num_betas > 0 && d->num_betas <= 10, "smpl_create: V=%d betas=%d", d->num_verts,
+             d->num_betas);
+  THMR_CHECK(d->v_template && d->shapedirs && d->posedirs && d->J_regressor && d->lbs_weights && d->parents_host &&
+                 d->extra_vertex_ids_host && d->joint_map_host,
+             "smpl_create: missing tensor");
+  thmr_smpl* s = new (std::nothrow) thmr_smpl();
+  if (!s) return fail(THMR_ERR_NOMEM, "smpl_create: out of host memory");
+  SmplModel& m = s->m;
+  const int V = d->num_verts, nb = d->num_betas;
+  m.V = V; m.nb = nb; m.n_extra = d->joint_regressor_extra ? d->n_extra : 0;
+  auto bail = [&](int code) { thmr_smpl_destroy(s); return code; };
+#define SM_TRY(e) do { int _r = (e); if (_r != THMR_OK) return bail(_r); } while (0)
+  SM_TRY(dev_clone(&m.v_template, d->v_template, static_cast<size_t>(V) * 3));
+  SM_TRY(dev_clone(&m.shapedirs, d->shapedirs, static_cast<size_t>(V) * 3 * nb));
+  for (int j = 0; j < kSmplJ; ++j) m.parents[j] = d->parents_host[j];
+  SM_TRY(dev_upload(&s->parents_dev, std::vector<int>(m.parents, m.parents + kSmplJ)));
+  // J_template / J_shapedirs
+  float* Jreg = nullptr;
+  SM_TRY(dev_clone(&Jreg, d->J_regressor, static_cast<size_t>(kSmplJ) * V));
+  SM_TRY(dev_alloc(&m.J_template, kSmplJ * 3));
+  SM_TRY(dev_alloc(&m.J_shapedirs, static_cast<size_t>(kSmplJ) * 3 * nb));
+  smpl_jreg_kernel<<<kSmplJ * 3 * (nb + 1), 256>>>(Jreg, m.v_template, m.shapedirs, m.J_template, m.J_shapedirs, V, nb);
+  // posedirs -> transposed split fp16
+  float* pd = nullptr;
+  SM_TRY(dev_clone(&pd, d->posedirs, static_cast<size_t>(kSmplPF) * 3 * V));
+  SM_TRY(dev_alloc(&m.posedirsT, static_cast<size_t>(3) * V * 3 * kSmplPFPad));
+  {
+    const long n = static_cast<long>(3) * V * kSmplPFPad;
+    smpl_pack_posedirs_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(pd, m.posedirsT, 3 * V);
+  }
+  cudaError_t ce = cudaDeviceSynchronize();
+  cudaFree(Jreg);
+  cudaFree(pd);
+  if (ce != cudaSuccess) return bail(fail(THMR_ERR_CUDA, "smpl_create: %s", cudaGetErrorString(ce)));
+  // skinning weights -> ELL
+  {
+    std::vector<float> W(static_cast<size_t>(V) * kSmplJ);
+    if (cudaMemcpy(W.data(), d->lbs_weights, W.size() * sizeof(float), cudaMemcpyDefault) != cudaSuccess)
+      return bail(fail(THMR_ERR_CUDA, "smpl_create: copy lbs_weights"));
+    int ell = 1;
+    for (int v = 0; v < V; ++v) {
+      int n = 0;
+      for (int j = 0; j < kSmplJ; ++j) n += (W[static_cast<size_t>(v) * kSmplJ + j] != 0.f);
+      ell = std::max(ell, n);
+    }
+    std::vector<int> idx(static_cast<size_t>(V) * ell, 0);
+    std::vector<float> val(static_cast<size_t>(V) * ell, 0.f);
+    for (int v = 0; v < V; ++v) {
+      int n = 0;
+      for (int j = 0; j < kSmplJ; ++j) {
+        const float w = W[static_cast<size_t>(v) * kSmplJ + j];
+        if (w != 0.f) { idx[static_cast<size_t>(v) * ell + n] = j; val[static_cast<size_t>(v) * ell + n] = w; ++n; }
+      }
+    }
+    m.ell = ell;
+    SM_TRY(dev_upload(&m.w_idx, idx));
+    SM_TRY(dev_upload(&m.w_val, val));
+  }
+  // extra joint regressor -> CSR
+  {
+    std::vector<int> ptr(1, 0), idx;
+    std::vector<float> val;
+    if (m.n_extra > 0) {
+      std::vector<float> Jx(static_cast<size_t>(m.n_extra) * V);
+      if (cudaMemcpy(Jx.data(), d->joint_regressor_extra, Jx.size() * sizeof(float), cudaMemcpyDefault) != cudaSuccess)
+        return bail(fail(THMR_ERR_CUDA, "smpl_create: copy joint_regressor_extra"));
+      for (int r = 0; r < m.n_extra; ++r) {
+        for (int v = 0; v < V; ++v) {
+          const float w = Jx[static_cast<size_t>(r) * V + v];
+          if (w != 0.f) { idx.push_back(v); val.push_back(w); }
+        }
+        ptr.push_back(static_cast<int>(idx.size()));
+      }
+    }
+    SM_TRY(dev_upload(&m.jx_ptr, ptr));
+    SM_TRY(dev_upload(&m.jx_idx, idx));
+    SM_TRY(dev_upload(&m.jx_val, val));
+  }
+  for (int i = 0; i < 21; ++i)
+    if (d->extra_vertex_ids_host[i] < 0 || d->extra_vertex_ids_host[i] >= V)
+      return bail(fail(THMR_ERR_INVALID, "smpl_create: extra vertex id %d out of range", d->extra_vertex_ids_host[i]));
+  SM_TRY(dev_upload(&m.extra_vid, std::vector<int>(d->extra_vertex_ids_host, d->extra_vertex_ids_host + 21)));
+  SM_TRY(dev_upload(&m.joint_map, std::vector<int>(d->joint_map_host, d->joint_map_host + 25)));
+#undef SM_TRY
+  *out = s;
+  return THMR_OK;
+}
+
+size_t thmr_smpl_workspace_bytes(const thmr_smpl* s, int batch) {
+  if (!s || batch <= 0) return 0;
+  Bump bp(nullptr);
+  SmplWs ws;
+  smpl_carve(bp, s->m, batch, &ws);
+  return (bp.off + 1023) & ~size_t(1023);
+}
+
+int thmr_lbs(const thmr_smpl* s, const float* pose, int pose2rot, const float* betas, int B, float* verts,
+             float* joints, void* workspace, void* stream) {
+  THMR_CHECK(s && pose && betas && verts && workspace && B > 0, "lbs: bad argument");
+  Bump bp(workspace);
+  SmplWs ws;
+  smpl_carve(bp, s->m, B, &ws);
+  return smpl_run(s, pose, pose2rot, betas, B, verts, joints, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, ws,
+                  nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int thmr_smpl_forward(const thmr_smpl* s, const float* rotmats, const float* betas, int B, float* verts, float* joints,
+                      const float* pred_cam, float focal_length, float image_size, float* cam_t, float* focal_out,
+                      float* kp2d, void* workspace, void* stream) {
+  THMR_CHECK(s && rotmats && betas && verts && joints && workspace && B > 0, "smpl_forward: bad argument");
+  THMR_CHECK(!pred_cam || (cam_t && focal_out && kp2d), "smpl_forward: pred_cam given without camera outputs");
+  Bump bp(workspace);
+  SmplWs ws;
+  smpl_carve(bp, s->m, B, &ws);
+  return smpl_run(s, rotmats, 0, betas, B, verts, nullptr, joints, pred_cam, focal_length, image_size, cam_t, focal_out,
+                  kp2d, ws, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------ engine
+int thmr_engine_create(const thmr_config* cfg, const thmr_weights* w, const thmr_smpl* smpl, thmr_engine** out) {
+  THMR_CHECK(cfg && w && smpl && out, "engine_create: null argument");
+  THMR_CHECK(cfg->vit_dim == cfg->vit_heads * kAttHeadDim, "engine_create: head_dim must be %d", kAttHeadDim);
+  const int gh = (cfg->image_size + 2 * cfg->patch_pad - cfg->patch) / cfg->patch + 1;
+  const int gw = (cfg->crop_w + 2 * cfg->patch_pad - cfg->patch) / cfg->patch + 1;
+  THMR_CHECK(gh * gw == kAttTokens, "engine_create: %dx%d patches != %d tokens", gh, gw, kAttTokens);
+  THMR_CHECK(cfg->dec_dim_head == 64 && cfg->dec_heads <= 8, "engine_create: decoder heads must be <=8 x 64");
+  THMR_CHECK(cfg->n_upsample >= 1 && cfg->n_upsample <= 8 && cfg->tok_depth >= 1 && cfg->tok_depth <= 8,
+             "engine_create: tokenizer depth");
+  THMR_CHECK(cfg->upsample_sizes[cfg->n_upsample - 1] == cfg->tok_joints, "engine_create: last upsample != joints");
+  THMR_CHECK(cfg->tok_width % 64 == 0 && cfg->code_dim % 64 == 0 && cfg->token_class_num % 8 == 0 &&
+                 cfg->token_class_num <= 2048 && cfg->token_num % 8 == 0,
+             "engine_create: tokenizer dims");
+  int maxdil = 1;
+  for (int k = 0; k < cfg->tok_depth - 1; ++k) maxdil *= cfg->tok_dilation_rate;
+  THMR_CHECK(maxdil <= kTokPad, "engine_create: dilation %d exceeds sequence padding %d", maxdil, kTokPad);
+  THMR_CHECK(smpl->m.nb <= 10 && smpl->m.n_extra + 25 <= 64, "engine_create: SMPL model shape");
+  THMR_CHECK(w->blocks_host && w->dec_host && w->mixer_host, "engine_create: missing layer arrays");
+  thmr_engine* e = new (std::nothrow) thmr_engine();
+  if (!e) return fail(THMR_ERR_NOMEM, "engine_create: out of host memory");
+  e->cfg = *cfg;
+  e->w = *w;
+  e->blocks.assign(w->blocks_host, w->blocks_host + cfg->vit_depth);
+  e->dec.assign(w->dec_host, w->dec_host + cfg->dec_depth);
+  e->mixer.assign(w->mixer_host, w->mixer_host + cfg->cls_blocks);
+  e->w.blocks_host = nullptr; e->w.dec_host = nullptr; e->w.mixer_host = nullptr;
+  e->smpl = smpl;
+  *out = e;
+  return THMR_OK;
+}
+
+void thmr_engine_destroy(thmr_engine* e) { delete e; }
+
+size_t thmr_engine_workspace_bytes(const thmr_engine* e, int max_batch) {
+  if (!e || max_batch <= 0) return 0;
+  int st;
+  return engine_build(const_cast<thmr_engine*>(e), nullptr, max_batch, false, &st, nullptr);
+}
+
+static int engine_prepare(thmr_engine* e, int B, void* workspace, cudaStream_t st) {
+  THMR_CHECK(e && workspace && B > 0, "engine_forward: bad argument");
+  THMR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "engine_forward: workspace not 1024-byte aligned");
+  if (e->ws != workspace || e->B != B) {
+    int status = THMR_OK;
+    e->ws = nullptr;
+    engine_build(e, workspace, B, true, &status, st);
+    if (status != THMR_OK) { e->steps.clear(); return status; }
+    e->ws = workspace;
+    e->B = B;
+  }
+  return THMR_OK;
+}
+
+int thmr_engine_forward(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
+                        void* stream) {
+  THMR_CHECK(img && out, "engine_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  THMR_TRY(engine_prepare(e, B, workspace, st));
+  RunCtx ctx{img, *out, nullptr};
+  for (auto& step : e->steps) THMR_TRY(step(ctx, st));
+  return THMR_OK;
+}
+
+int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream) {
+  THMR_CHECK(img && tokens, "vit_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  THMR_TRY(engine_prepare(e, B, workspace, st));
+  RunCtx ctx{img, thmr_outputs{}, tokens};
+  for (size_t i = 0; i < e->vit_steps; ++i) THMR_TRY(e->steps[i](ctx, st));
+  return THMR_OK;
+}
+
+int thmr_engine_num_launches(const thmr_engine* e) {
+  if (!e) return 0;
+  // every step is one kernel except the SMPL tail (assemble + pose + blend GEMM + skin + joints = 5)
+  return e->steps.empty() ? 0 : static_cast<int>(e->steps.size()) + 4;
 }
 
 }  // extern "C"
