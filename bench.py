@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the full TokenHMR forward (BASELINE.json metric) on N B200s of one box.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5              # our engine (default)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        # one rank per GPU, weak scaling (64 images / rank)
+    python bench.py --impl reference --steps 3 --warmup 1       # reference arm: CPU fp32 forward on the host cores
+
+A "step" is one forward of the path over one synthetic batch: configs[1] of BASELINE.json
+(bs=64 synthetic 256x256 inputs cropped to 256x192, ViT-H/16 + token decoder + SMPL, fp16 operands / fp32
+accumulate), random-init weights of the release architecture (no checkpoints exist offline).
+
+JSON line (rank 0):  value = whole-job images/s with the batch already resident in HBM (CUDA-graph replay of
+the engine forward; on N > 1 GPUs the per-step NCCL all-gather of the outputs is inside the timed region),
+e2e = the same through the public API TokenHMREngine.forward(batch) with pinned HOST input (H2D inside) and a
+D2H read-back of the results a caller consumes, roofline = live per-kernel-family accounting from the engine's
+timed replay, cpu_baseline = the oracle (CPU restatement of the reference) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec (256x192) at bs=64 per GPU, full TokenHMR forward"
+FLOP_PER_IMAGE = 252.10e9
+PER_GPU_BATCH = 64
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = max([float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()] or [0.0])
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_forward_rate(sample_images: int, repeats: int, threads: int):
+    """The oracle (fp32 CPU restatement of the reference forward) timed on the host cores."""
+    import torch
+    from oracle import tokenhmr_oracle as O
+    from tokenhmr_b200 import synth
+    from tokenhmr_b200.config import release_config
+    torch.set_num_threads(threads)
+    cfg = release_config()
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    img = synth.make_images(sample_images, cfg)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t = time.perf_counter()
+            O.forward(sd, smpl, img, cfg)
+            times.append(time.perf_counter() - t)
+    return sample_images / min(times), times
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  /root/reference does not exist on the GPU box and the
+    reference package cannot be installed offline (pytorch_lightning / smplx / yacs missing), so this
+    times the oracle port, which is bit-identical to the reference modules (tests/test_oracle_pinned.py)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    sample = 4                                   # images per step: a bounded sample of the bs=64 workload
+    from oracle import tokenhmr_oracle as O
+    from tokenhmr_b200 import synth
+    from tokenhmr_b200.config import release_config
+    torch.set_num_threads(threads)
+    cfg = release_config()
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    img = synth.make_images(sample, cfg)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(sd, smpl, img, cfg)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, smpl, img, cfg)
+        dt = time.perf_counter() - t
+    value = sample * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)",
+                   "sample": f"{sample} images per step"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} images/step x {args.steps} steps, fp32 eager torch, all host threads"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from tokenhmr_b200 import synth
+    from tokenhmr_b200._lib import lib
+    from tokenhmr_b200.config import release_config
+    from tokenhmr_b200.dist import ShardedTokenHMR
+    from tokenhmr_b200.engine import TokenHMREngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    cfg = release_config()
+    B = PER_GPU_BATCH
+    model = TokenHMREngine(cfg, synth.make_state_dict(cfg), synth.make_smpl(cfg), device=dev, use_cuda_graph=True)
+    sharded = ShardedTokenHMR(model)
+    img_host = synth.make_images(B, cfg, seed=rank).pin_memory()
+    img_dev = img_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident throughput: graph replay (+ all-gather when world > 1)
+    def step_resident():
+        out = model({"img": img_dev})
+        return sharded.all_gather(out) if world > 1 else out
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B * 1e3 / ms_step
+
+    # ---- (2) end to end through the public API: pinned host input -> H2D -> forward -> D2H of the results
+    consumed = ["pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t"]   # demo.py:80-118, pose_utils.py:217-239
+    host_out = {}
+
+    def step_e2e():
+        out = model({"img": img_host})
+        if world > 1:
+            out = sharded.all_gather(out)
+        for k in consumed:
+            if k not in host_out:
+                host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * B * 1e3 / ms_e2e
+    h2d = img_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host_out.values())
+
+    # ---- (3) live per-kernel-family accounting (rank 0): timed eager replay of the same forward
+    roofline, families = None, None
+    if rank == 0:
+        agg = {}
+        for _ in range(3):
+            for name, ms, fl, by in model.profile(img_dev):
+                a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+                a[0] += ms; a[1] += fl; a[2] += by; a[3] += 1
+        peaks = measured_peaks()
+        tot_ms = sum(a[0] for a in agg.values())
+        families = {k: {"ms_per_step": a[0] / 3, "share": a[0] / tot_ms,
+                        "tflops": (a[1] / (a[0] * 1e-3) / 1e12) if a[1] and a[0] else None} for k, a in agg.items()}
+        gemm = [a for k, a in agg.items() if k.endswith("_gemm")]
+        g_ms, g_fl = sum(a[0] for a in gemm), sum(a[1] for a in gemm)
+        achieved = g_fl / (g_ms * 1e-3) / 1e12
+        roofline = {"kernel": "gemm_f16_tn_kernel (tcgen05, all ViT/decoder GEMM launches)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
+                    "share_of_step": g_ms / tot_ms, "traffic": None,
+                    "whole_step_tflops_per_gpu": B * FLOP_PER_IMAGE / (ms_step * 1e-3) / 1e12}
+
+    # ---- (4) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, times = cpu_forward_rate(sample_images=8, repeats=2, threads=threads)
+        cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"8 of the 64 images, best of 2 fp32 eager-torch forwards of the oracle ({min(times):.1f}s)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)",
+                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world} + 1 all-gather of outputs",
+                       "weights": "random-init release architecture (seed 1234)",
+                       "l2": "1.4 GB of fp16 weights + 0.6 GB of activations stream through the 126 MB L2 every step (inputs larger than L2, no flush needed)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "read_back": consumed},
+            "gpu_launches": args.steps * model.num_launches(),
+            "launches_per_step": model.num_launches(),
+            "clocks": clocks, "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -231,6 +231,13 @@ int thmr_engine_forward(thmr_engine* e, const float* img, int B, const thmr_outp
                         void* stream);
 /* Number of kernels one forward launches (for bench.py's gpu_launches). */
 int thmr_engine_num_launches(const thmr_engine* e);
+/* Timed replay for roofline accounting: the forward is a list of launch groups ("steps"); this runs one
+ * forward with a CUDA event between steps (synchronises the stream at the end) and returns per-step
+ * milliseconds.  thmr_engine_step_info gives each step's label and algorithmic FLOPs / HBM bytes. */
+int thmr_engine_num_steps(const thmr_engine* e);
+int thmr_engine_step_info(const thmr_engine* e, int i, const char** name, double* flops, double* bytes);
+int thmr_engine_profile(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
+                        void* stream, float* step_ms, int cap);
 /* Backbone only: ViT.forward [vit.py:341-343]: img -> tokens fp32 [B,192,D] (token-major). */
 int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream);
 

@@ -208,6 +208,33 @@ def tokenizer_decode(sd: Dict[str, Tensor], probs: Tensor, cfg, nm: Numerics,
     return x.permute(0, 2, 1)                                                       # postprocess :156-159
 
 
+def vq_quantize(x: Tensor, codebook: Tensor, chunk: int = 65536) -> Tensor:
+    """QuantizeEMAReset.quantize (quantize_cnn.py:80-86): first-minimum index of
+    sum(x^2) - 2 x @ codebook^T + sum(codebook^2); row-chunked (identical per-row arithmetic) so that 1 M
+    queries do not materialise an 8 GB distance matrix."""
+    k_w = codebook.t()
+    c2 = torch.sum(k_w ** 2, dim=0, keepdim=True)
+    out = []
+    for i in range(0, x.shape[0], chunk):
+        xc = x[i:i + chunk]
+        distance = torch.sum(xc ** 2, dim=-1, keepdim=True) - 2 * torch.matmul(xc, k_w) + c2
+        out.append(torch.min(distance, dim=-1)[1])
+    return torch.cat(out)
+
+
+def vq_top2_gap(x: Tensor, codebook: Tensor) -> Tensor:
+    """Distance gap between the best and second-best code per query (near-tie detector for index parity)."""
+    k_w = codebook.t()
+    d = torch.sum(x ** 2, dim=-1, keepdim=True) - 2 * torch.matmul(x, k_w) + torch.sum(k_w ** 2, dim=0, keepdim=True)
+    t = d.topk(2, dim=-1, largest=False).values
+    return t[:, 1] - t[:, 0]
+
+
+def vq_dequantize(idx: Tensor, codebook: Tensor) -> Tensor:
+    """QuantizeEMAReset.dequantize (quantize_cnn.py:88-90)."""
+    return F.embedding(idx, codebook)
+
+
 def rot6d_to_rotmat(x: Tensor) -> Tensor:
     """geometry.py:64-84: Gram-Schmidt, rows of the result are b1, b2, b3.  (N*6,) -> (N,3,3)."""
     x = x.reshape(-1, 2, 3).permute(0, 2, 1).contiguous()

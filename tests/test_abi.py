@@ -1,0 +1,63 @@
+"""The C-ABI library builds, loads on a CPU-only host and exports every symbol include/tokenhmr_b200.h
+declares (no compute calls here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    text = (ROOT / "include" / "tokenhmr_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(thmr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(built_lib):
+    from tokenhmr_b200._lib import SIGNATURES
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in the header but not exported"
+        assert n in SIGNATURES, f"{n} has no ctypes signature"
+    assert set(SIGNATURES) == set(names)
+
+
+def test_version_and_error_string(built_lib):
+    assert built_lib.thmr_abi_version() >= 2
+    assert isinstance(built_lib.thmr_last_error(), bytes)
+
+
+def test_struct_layouts_match_header_field_counts():
+    """Cheap guard against header / ctypes drift: field names of every mirrored struct appear in the header."""
+    from tokenhmr_b200 import _lib
+    text = (ROOT / "include" / "tokenhmr_b200.h").read_text()
+    for cls in (_lib.SmplDesc, _lib.Config, _lib.VitBlock, _lib.DecLayer, _lib.MixerBlock, _lib.Conv, _lib.Weights,
+                _lib.Outputs):
+        for name, _ in cls._fields_:
+            assert re.search(rf"\b{name}\b", text), f"{cls.__name__}.{name} not in header"
+    assert ctypes.sizeof(_lib.Outputs) == 12 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from tokenhmr_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.ThmrError, match="no non-CUDA fallback"):
+        _lib.lib()
+
+
+def test_engine_refuses_cpu_device():
+    from tokenhmr_b200 import _lib
+    from tokenhmr_b200.config import tiny_config
+    from tokenhmr_b200.engine import TokenHMREngine
+    with pytest.raises(_lib.ThmrError, match="no CPU fallback"):
+        TokenHMREngine(tiny_config(), {}, {}, device="cpu")
+
+
+def test_product_never_imports_the_oracle():
+    for f in (ROOT / "tokenhmr_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,62 @@
+"""Host-side logic: config arithmetic, synthetic generators, checkpoint key handling, shard ranges."""
+import torch
+
+from tokenhmr_b200 import synth
+from tokenhmr_b200.config import release_config, tiny_config
+from tokenhmr_b200.dist import shard_range
+from tokenhmr_b200.weights import strip_checkpoint
+
+
+def test_release_config_matches_reference_numbers():
+    c = release_config()
+    assert (c.grid_h, c.grid_w, c.num_tokens, c.head_dim, c.crop_x0) == (16, 12, 192, 80, 32)
+    assert c.upsample_sizes == [125, 90, 55, 21]          # vanilla_pose_vqvae.py:139
+    assert c.dec_inner == 512 and c.npose == 144
+
+
+def test_synthetic_state_dict_shapes_and_parameter_counts():
+    c = tiny_config(vit_depth=2)
+    sd = synth.make_state_dict(c)
+    per_block = sum(v.numel() for k, v in sd.items() if k.startswith("backbone.blocks.0."))
+    rest = sum(v.numel() for k, v in sd.items() if k.startswith("backbone.") and ".blocks." not in k)
+    assert per_block * 32 + rest == 630_912_000          # SURVEY.md §8 header (ViT-H probe)
+    dec = sum(v.numel() for k, v in sd.items() if k.startswith("smpl_head.transformer."))
+    assert dec == 39_386_112
+    cls = sum(v.numel() for k, v in sd.items() if k.startswith("smpl_head.decpose."))
+    assert cls == 10_870_080
+    tok = sum(v.numel() for k, v in sd.items() if k.startswith("tokenizer.decoder."))
+    assert tok == 6_436_870
+    assert sd["tokenizer.quantizer.codebook"].shape == (2048, 256)
+
+
+def test_synthetic_generation_is_deterministic_and_nested():
+    a = synth.make_state_dict(tiny_config(vit_depth=1))
+    b = synth.make_state_dict(tiny_config(vit_depth=2))
+    for k, v in a.items():
+        assert torch.equal(v, b[k]), k
+
+
+def test_synthetic_smpl_is_well_formed():
+    m = synth.make_smpl(tiny_config(num_verts=500))
+    assert torch.allclose(m["lbs_weights"].sum(1), torch.ones(500), atol=1e-6)
+    assert (m["lbs_weights"] > 0).sum(1).max() <= 4
+    assert torch.allclose(m["J_regressor"].sum(1), torch.ones(24), atol=1e-6)
+    assert m["parents"][0] == -1 and int(m["extra_vertex_ids"].max()) < 500
+
+
+def test_strip_checkpoint_prefixes():
+    ck = {"backbone.pos_embed": torch.zeros(1), "smpl_head.deccam.bias": torch.zeros(3), "discriminator.x": torch.zeros(1)}
+    net = {"decoder.decoder.0.weight": torch.zeros(1), "quantizer.codebook": torch.zeros(1),
+           "decoder.body_model.faces": torch.zeros(1), "encoder.x": torch.zeros(1)}
+    out = strip_checkpoint(ck, net)
+    assert set(out) == {"backbone.pos_embed", "smpl_head.deccam.bias", "tokenizer.decoder.decoder.0.weight",
+                        "tokenizer.quantizer.codebook"}
+
+
+def test_shard_range_covers_batch_contiguously():
+    for gb, world in [(512, 8), (10, 4), (3, 8), (64, 1)]:
+        spans = [shard_range(gb, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -123,6 +123,11 @@ SIGNATURES = {
     "thmr_engine_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "thmr_engine_forward": (c_int, [c_void_p, c_void_p, c_int, POINTER(Outputs), c_void_p, c_void_p]),
     "thmr_engine_num_launches": (c_int, [c_void_p]),
+    "thmr_engine_num_steps": (c_int, [c_void_p]),
+    "thmr_engine_step_info": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(ctypes.c_double),
+                                      POINTER(ctypes.c_double)]),
+    "thmr_engine_profile": (c_int, [c_void_p, c_void_p, c_int, POINTER(Outputs), c_void_p, c_void_p,
+                                    POINTER(c_float), c_int]),
     "thmr_engine_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

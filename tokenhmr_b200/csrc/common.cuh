@@ -61,26 +61,29 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 2D fp16 tensor map over a row-major [rows, cols] matrix with row pitch ld (elements), tile box
-// [box_rows, box_cols]; swizzle chosen by the caller (box_cols * 2 bytes must equal the swizzle span).
-inline int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                            uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+// 2D tensor map over a row-major [rows, cols] matrix with row pitch ld (elements), tile box
+// [box_rows, box_cols]; swizzle chosen by the caller (box_cols * elem bytes must not exceed the swizzle span).
+inline int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows,
+                        uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(THMR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   THMR_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p not 16B aligned", base);
-  THMR_CHECK((ld * 2) % 16 == 0, "tensor map row pitch %llu elements is not a multiple of 16 bytes",
+  THMR_CHECK((ld * elem_bytes) % 16 == 0, "tensor map row pitch %llu elements is not a multiple of 16 bytes",
              (unsigned long long)ld);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * 2};
+  cuuint64_t gstr[1] = {ld * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(THMR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
   return THMR_OK;
+}
+inline int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, rows, cols, ld, box_rows, box_cols, swz);
 }
 
 inline int num_sms() {

@@ -29,6 +29,15 @@ struct RunCtx {
 
 using StepFn = std::function<int(const RunCtx&, cudaStream_t)>;
 
+// One launch group of the forward: a label (kernel family + role) and its algorithmic work, so that a timed
+// replay (thmr_engine_profile) can attribute device time and compute roofline fractions live.
+struct Step {
+  StepFn fn;
+  const char* name;
+  double flops;   // algorithmic FLOPs (2*MAC) of tensor-core work, 0 for bandwidth-bound kernels
+  double bytes;   // algorithmic HBM bytes for bandwidth-bound kernels, 0 otherwise
+};
+
 struct Bump {
   uint8_t* base;
   size_t off = 0;
@@ -102,7 +111,7 @@ struct thmr_engine {
   // plan cache
   void* ws = nullptr;
   int B = 0;
-  std::vector<thmr::StepFn> steps;
+  std::vector<thmr::Step> steps;
   size_t vit_steps = 0;  // steps [0, vit_steps) = backbone
 };
 
@@ -175,14 +184,20 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   if (!build) return total;
 
   // ---------------------------------------------------------------- steps
-  std::vector<StepFn>& S = e->steps;
-  S.clear();
+  e->steps.clear();
+  struct StepList {
+    std::vector<Step>& v;
+    const char* name = "";
+    double flops = 0, bytes = 0;
+    void tag(const char* n, double f = 0, double b = 0) { name = n; flops = f; bytes = b; }
+    void push_back(StepFn fn) { v.push_back(Step{std::move(fn), name, flops, bytes}); }
+    size_t size() const { return v.size(); }
+  } S{e->steps};
   int err = THMR_OK;
   auto add_gemm = [&](const GemmDesc& d) {
     GemmPlan plan;
     const int s = gemm_make_plan(d, &plan);
     if (s != THMR_OK) { err = s; return; }
-    S.push_back([plan](const RunCtx&, cudaStream_t st) { return gemm_launch(plan, st); });
   };
   auto linear = [&](const __half* A, int lda, int rows, const void* Wt, int N, int K, const float* bias, int act,
                     float* o32, __half* o16, const float* resid = nullptr) {
@@ -196,6 +211,8 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   };
   auto ln = [&](const float* in, const float* g, const float* b, __half* o16, float* o32, int R, int C, float eps,
                 int relu, int out_t) {
+    S.flops = 0;
+    S.bytes = static_cast<double>(R) * C * (4 + (o16 ? 2 : 0) + (o32 ? 4 : 0));
     S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
       return layernorm_launch(in, g, b, o16, 0, o32, R, C, eps, relu, out_t, st);
     });
@@ -204,6 +221,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   // ---- ViT backbone (vit.py:320-343)
   {
     const int S_ = c.image_size, x0 = (c.image_size - c.crop_w) / 2, Wc = c.crop_w, P = c.patch, pad = c.patch_pad;
+    S.tag("vit.patch_im2col", 0, static_cast<double>(B) * 3 * c.image_size * c.crop_w * 4 + static_cast<double>(M) * KP * 2);
     S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
       const long total_t = static_cast<long>(B) * gh * gw * 3 * P;
       im2col_patch_kernel<<<static_cast<unsigned>((total_t + 255) / 256), 256, 0, st>>>(r.img, a0, B, S_, x0, Wc, P, pad,
@@ -211,6 +229,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
       THMR_CUDA(cudaGetLastError());
       return THMR_OK;
     });
+    S.tag("vit.patch_embed_gemm");
     GemmDesc d;
     d.A = a0; d.lda = KP; d.a_rows = M;
     d.B = static_cast<const __half*>(w.patch_w); d.ldb = KP;
@@ -221,20 +240,29 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   }
   for (int i = 0; i < c.vit_depth; ++i) {
     const thmr_vit_block& bw = e->blocks[i];
+    S.tag("vit.layernorm");
     ln(x, bw.ln1_g, bw.ln1_b, xn, nullptr, M, D, c.vit_ln_eps, 0, 0);
+    S.tag("vit.qkv_gemm");
     linear(xn, D, M, bw.qkv_w, 3 * D, D, bw.qkv_b, kActNone, nullptr, qkv);
     {
+      // 4*N*N*d FLOPs per head (QK^T + PV); Q,K,V read + O written once in fp16
+      S.tag("vit.attention", 4.0 * B * H * 192.0 * 192.0 * 80.0, 4.0 * M * D * 2);
       AttnPlan ap;
       const int s = attention_make_plan(qkv, 3 * D, B, H, ao, D, nullptr, &ap);
       if (s != THMR_OK) err = s;
-      S.push_back([ap](const RunCtx&, cudaStream_t st) { return attention_launch(ap, st); });
+      S.push_back([ap](const RunCtx&, cudaStream_t st) -> int { return attention_launch(ap, st); });
     }
+    S.tag("vit.proj_gemm");
     linear(ao, D, M, bw.proj_w, D, D, bw.proj_b, kActNone, x, nullptr, x);
+    S.tag("vit.layernorm");
     ln(x, bw.ln2_g, bw.ln2_b, xn, nullptr, M, D, c.vit_ln_eps, 0, 0);
+    S.tag("vit.fc1_gelu_gemm");
     linear(xn, D, M, bw.fc1_w, c.vit_mlp_ratio * D, D, bw.fc1_b, kActGelu, nullptr, hbuf);
+    S.tag("vit.fc2_gemm");
     linear(hbuf, c.vit_mlp_ratio * D, M, bw.fc2_w, D, c.vit_mlp_ratio * D, bw.fc2_b, kActNone, x, nullptr, x);
   }
   {
+    S.tag("vit.layernorm", 0, static_cast<double>(M) * D * 6);
     const float* g = w.last_g; const float* b = w.last_b;
     const float eps = c.vit_ln_eps;
     S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
@@ -245,7 +273,9 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   e->vit_steps = S.size();
 
   // ---- decoder (pose_transformer.py:191-201,349-357): K/V of all layers in one GEMM
+  S.tag("dec.to_kv_gemm");
   linear(feat, D, M, w.kv_w, L * 2 * inner, D, nullptr, kActNone, nullptr, kv);
+  S.tag("dec.token_ops");
   {
     const float* t0 = w.token0;
     S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
@@ -288,6 +318,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   linear(y16, E, B, w.readout_w, 32, E, w.readout_b, kActNone, readout, nullptr);
 
   // ---- token classifier (token_classifier.py:89-104)
+  S.tag("cls.mixer_ops");
   linear(y16, E, B, w.mt_w, TN * CH, E, w.mt_b, kActNone, mt32, nullptr);
   ln(mt32, w.mt_ln_g, w.mt_ln_b, nullptr, cx, B, TN * CH, c.ln_eps, 1, 0);   // FCBlock: LN + ReLU -> x (B*T, H)
   for (int i = 0; i < c.cls_blocks; ++i) {
@@ -316,6 +347,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     return softmax_rows_launch(logits, p32, p16, B * TN, NC, TN, Lp0, PAD, st);
   });
 
+  S.tag("tok.decoder_ops");
   // ---- tokenizer: soft codebook lookup + Conv1d decoder (vanilla_pose_vqvae.py:294-297, 135-154)
   {
     GemmDesc d;   // dequantize_logits on the padded layout (pad rows are zero -> zero output rows)
@@ -364,6 +396,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   conv(bufA, Lcur, W, w.conv_post, W, 1, 3, kActNone, 0, nullptr, 0, bufB, nullptr);
   conv(bufB, Lcur, W, w.conv_out, 6, 1, 3, kActNone, 0, out6, 8, nullptr, nullptr);
 
+  S.tag("smpl.lbs");
   // ---- read-out assembly, 6D -> rotation (token_head.py:103-128), SMPL + projection (tokenhmr.py:162-187)
   {
     const float* ip = w.init_pose; const float* ib = w.init_betas; const float* ic = w.init_cam;

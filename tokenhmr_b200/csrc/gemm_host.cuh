@@ -6,9 +6,10 @@
 namespace thmr {
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   GemmParams p;
   int bn;
+  int epi;
   int grid;
 };
 
@@ -27,23 +28,37 @@ struct GemmDesc {
   float alpha = 1.0f;
   long long* argmin_out = nullptr; const float* row_sq = nullptr; const float* col_sq = nullptr;
   int force_bn = 0;
+  int force_epi = -1;  // 0 forces the generic epilogue (tests)
 };
 
-inline int pick_bn(int M, int N, int force) {
+// Which epilogue can serve this GEMM (see gemm_tcgen05.cuh).
+inline int pick_epi(const GemmDesc& d) {
+  const bool plain = !d.argmin_out && d.seq_pitch == 0 && d.alpha == 1.0f && d.resid_mod == 0 && !d.act32 &&
+                     d.N % 8 == 0 && d.M >= kGemmBM && (!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
+  if (!plain) return kEpiGeneric;
+  if (d.out16 && !d.out32 && !d.resid && d.ld16 % 8 == 0) return kEpiStore16;
+  if (d.out32 && !d.out16 && d.resid == d.out32 && d.ldr == d.ld32 && d.act == kActNone && d.ld32 % 4 == 0)
+    return kEpiAdd32;
+  return kEpiGeneric;
+}
+
+// Tile width: the main loop is L2-feed bound (every k-block moves (128 + BN) * 128 bytes for 128 * BN * 64 MACs),
+// so wide tiles win unless they leave SMs idle.  Cost model per k-block in cycles: max(MMA, L2 feed at ~40 B/clk/SM).
+inline int pick_bn(int M, int N, int force, int epi) {
   if (force) return force;
   const int sms = num_sms();
   const int tm = (M + kGemmBM - 1) / kGemmBM;
   int best = 256;
-  long best_cost = -1;
+  double best_cost = -1;
   const int cands[4] = {256, 128, 64, 32};
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
+    if (epi != kEpiGeneric && bn < 128) continue;
     const long tiles = static_cast<long>(tm) * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
-    // MMA time per tile scales with BN (M fixed at 128); + fixed per-tile cost; narrow tiles
-    // are smem-bandwidth bound (A re-read per column block), so weight them up.
-    const long per_tile = bn + 24 + (bn < 128 ? (128 - bn) / 2 : 0);
-    const long cost = waves * per_tile;
+    const double mma = 2.0 * bn;
+    const double feed = (128.0 + bn) * 128.0 / 40.0;
+    const double cost = waves * ((mma > feed ? mma : feed) + 40.0);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -52,7 +67,10 @@ inline int pick_bn(int M, int N, int force) {
 inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: bad shape %dx%dx%d", d.M, d.N, d.K);
   THMR_CHECK(d.out32 || d.out16 || d.argmin_out, "gemm: no output");
-  const int bn = pick_bn(d.M, d.N, d.force_bn);
+  int epi = pick_epi(d);
+  if (d.force_bn && d.force_bn < 128) epi = kEpiGeneric;
+  if (d.force_epi >= 0) epi = d.force_epi == kEpiGeneric ? kEpiGeneric : epi;
+  const int bn = pick_bn(d.M, d.N, d.force_bn, epi);
   THMR_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad block_n %d", bn);
   GemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -74,34 +92,52 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_TRY(make_tmap_2d_f16(&plan->tmA, d.A, d.a_rows, a_cols, d.lda, kGemmBM, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, bn, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   plan->bn = bn;
+  plan->epi = epi;
+  if (epi == kEpiStore16)
+    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, 32, 64,
+                          CU_TENSOR_MAP_SWIZZLE_128B));
+  else if (epi == kEpiAdd32)
+    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out32, d.M, d.N, d.ld32, 32, 32,
+                          CU_TENSOR_MAP_SWIZZLE_128B));
+  else
+    plan->tmC = plan->tmA;
   const long tiles_m = (d.M + kGemmBM - 1) / kGemmBM;
   const long tiles = d.argmin_out ? tiles_m : tiles_m * ((d.N + bn - 1) / bn);
   plan->grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   return THMR_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 inline int gemm_launch_t(const GemmPlan& plan, cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, EPI>;
   static bool configured = false;
   if (!configured) {
-    THMR_CUDA(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    THMR_CUDA(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    S::kTotal));
     configured = true;
   }
-  gemm_f16_tn_kernel<BN, STAGES><<<plan.grid, kGemmThreads, S::kTotal, stream>>>(plan.tmA, plan.tmB, plan.p);
+  gemm_f16_tn_kernel<BN, STAGES, EPI><<<plan.grid, kGemmThreads, S::kTotal, stream>>>(plan.tmA, plan.tmB, plan.tmC,
+                                                                                      plan.p);
   THMR_CUDA(cudaGetLastError());
   return THMR_OK;
 }
 
 inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  switch (plan.bn) {
-    case 256: return gemm_launch_t<256, 4>(plan, stream);
-    case 128: return gemm_launch_t<128, 6>(plan, stream);
-    case 64: return gemm_launch_t<64, 8>(plan, stream);
-    case 32: return gemm_launch_t<32, 8>(plan, stream);
+  if (plan.epi == kEpiStore16) {
+    if (plan.bn == 256) return gemm_launch_t<256, 4, kEpiStore16>(plan, stream);
+    if (plan.bn == 128) return gemm_launch_t<128, 6, kEpiStore16>(plan, stream);
+  } else if (plan.epi == kEpiAdd32) {
+    if (plan.bn == 256) return gemm_launch_t<256, 4, kEpiAdd32>(plan, stream);
+    if (plan.bn == 128) return gemm_launch_t<128, 6, kEpiAdd32>(plan, stream);
+  } else {
+    switch (plan.bn) {
+      case 256: return gemm_launch_t<256, 4, kEpiGeneric>(plan, stream);
+      case 128: return gemm_launch_t<128, 6, kEpiGeneric>(plan, stream);
+      case 64: return gemm_launch_t<64, 8, kEpiGeneric>(plan, stream);
+      case 32: return gemm_launch_t<32, 8, kEpiGeneric>(plan, stream);
+    }
   }
-  return fail(THMR_ERR_INVALID, "gemm: unsupported block_n %d", plan.bn);
+  return fail(THMR_ERR_INVALID, "gemm: unsupported block_n %d / epilogue %d", plan.bn, plan.epi);
 }
 
 }  // namespace thmr

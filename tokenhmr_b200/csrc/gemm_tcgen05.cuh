@@ -1,22 +1,30 @@
-// Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] * B[N,K]^T)
+// Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T)
 //   A (activations) and B (nn.Linear / conv weight, stored [out, in]) are both K-major fp16,
 //   accumulation is fp32 in TMEM.
 //
-//   warp 0   : TMA producer (one thread)       global -> 128B-swizzled smem ring
-//   warp 1   : MMA issuer   (one thread)       tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
-//   warp 2   : TMEM allocator / deallocator
-//   warps 4+ : epilogue                         tcgen05.ld -> bias / residual / activation -> global
+//   warp 0     : TMA producer (one thread)       global -> 128B-swizzled smem ring
+//   warp 1     : MMA issuer   (one thread)       tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 2     : TMEM allocator / deallocator
+//   warps 4-11 : epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns)
 //
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
-// The same kernel runs the implicit-GEMM Conv1d (k=3, dilated) of the pose-token decoder:
-// k-blocks are grouped in "taps", each tap reads the A rows shifted by a row offset
-// (TMA zero-fills rows that fall outside the tensor).
+//
+// Epilogue flavours (template EPI):
+//   kEpiGeneric : tcgen05.ld -> bias / residual / activation -> direct global stores; handles every option
+//                 (two outputs, residual tables, padded-sequence masking, row-argmin).  Used by the small-M tail.
+//   kEpiStore16 : act(acc + bias) -> fp16 -> 128B-swizzled smem -> TMA store            (QKV, fc1+GELU, to_kv)
+//   kEpiAdd32   : (acc + bias) fp32 -> swizzled smem -> TMA reduce-add into the output   (proj / fc2: x += ...)
+//                 the residual add happens in the L2 reduction unit, the residual is never read by the SM.
+//
+// The same kernel runs the implicit-GEMM Conv1d (k=3, dilated) of the pose-token decoder: k-blocks are
+// grouped in "taps", each tap reads the A rows shifted by a row offset (TMA zero-fills out-of-range rows).
 #pragma once
 #include "ptx.cuh"
 
 namespace thmr {
 
 enum : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+enum : int { kEpiGeneric = 0, kEpiStore16 = 1, kEpiAdd32 = 2 };
 
 struct GemmParams {
   int M, N, K;
@@ -69,26 +77,40 @@ struct TileIter {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 256;  // 4 control warps + 4 epilogue warps
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kGemmEpiWarps;  // 4 control warps + 8 epilogue warps
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 struct GemmSmem {
   static constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;
   static constexpr uint32_t kBBytes = BN * kGemmBK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kBarOffset = STAGES * kStageBytes;
-  static constexpr uint32_t kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+  static constexpr uint32_t kStagingOffset = STAGES * kStageBytes;              // 1024-aligned
+  static constexpr uint32_t kStagingBytes = (EPI == kEpiGeneric) ? 0 : kGemmEpiWarps * 4096;
+  static constexpr uint32_t kBarOffset = kStagingOffset + kStagingBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 1280 + 1024;  // barriers + argmin exchange, alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void named_bar_sync_64(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p) {
-  using S = GemmSmem<BN, STAGES>;
+                   const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using S = GemmSmem<BN, STAGES, EPI>;
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
+  static_assert(EPI == kEpiGeneric || BN >= 128, "TMA epilogues need BN >= 128 (two column halves of >= 64)");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,6 +119,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* xch_val = reinterpret_cast<float*>(smem + S::kBarOffset + 256);   // [128] argmin exchange
+  int* xch_idx = reinterpret_cast<int*>(xch_val + 128);                     // [128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +132,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != kEpiGeneric) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -116,7 +141,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], kGemmEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -182,136 +207,234 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec16 = p.out16 && (p.ld16 % 8 == 0);
-    const bool vec32 = (!p.out32 || p.ld32 % 4 == 0) && (!p.resid || p.ldr % 4 == 0);
-    float best = INFINITY;
-    long long best_idx = 0;
-    for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
-      const int m0 = it.m0(kGemmBM);
-      const int n0 = it.n0(BN);
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      bool row_zero = false;
-      if (p.seq_pitch > 0) {
-        const int r = row % p.seq_pitch;
-        row_zero = (r < p.seq_lo) || (r >= p.seq_hi);
-      }
-      const float* rrow = nullptr;
-      if (p.resid) rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldr;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+    if constexpr (EPI == kEpiGeneric) {
+      constexpr int kChunks = BN / 32;
+      constexpr int kChunksPerHalf = (kChunks + 1) / 2;
+      const bool vec16 = p.out16 && (p.ld16 % 8 == 0);
+      const bool vec32 = (!p.out32 || p.ld32 % 4 == 0) && (!p.resid || p.ldr % 4 == 0);
+      float best = INFINITY;
+      int best_idx = 0;
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+        const int m0 = it.m0(kGemmBM);
+        const int n0 = it.n0(BN);
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        bool row_zero = false;
+        if (p.seq_pitch > 0) {
+          const int r = row % p.seq_pitch;
+          row_zero = (r < p.seq_lo) || (r >= p.seq_hi);
+        }
+        const float* rrow = nullptr;
+        if (p.resid) rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldr;
+
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (p.argmin_out) {
-          if (row_ok && col0 < p.N) {
-            const float x2 = __ldg(p.row_sq + row);
+        for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+          const int c = half * kChunksPerHalf + cc;
+          if (c >= kChunks) break;
+          uint32_t v[32];
+          tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (p.argmin_out) {
+            if (row_ok && col0 < p.N) {
+              const float x2 = __ldg(p.row_sq + row);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < p.N) {
-                // same expression order as the reference: (sum x^2 - 2 x.c) + sum c^2
-                const float d = (x2 - 2.0f * (p.alpha * __uint_as_float(v[j]))) + __ldg(p.col_sq + col0 + j);
-                if (d < best) { best = d; best_idx = col0 + j; }
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < p.N) {
+                  // same expression order as the reference: (sum x^2 - 2 x.c) + sum c^2
+                  const float d = (x2 - 2.0f * (p.alpha * __uint_as_float(v[j]))) + __ldg(p.col_sq + col0 + j);
+                  if (d < best) { best = d; best_idx = col0 + j; }
+                }
               }
             }
-          }
-        } else if (row_ok && col0 < p.N) {
-          const bool full = (col0 + 32 <= p.N);
-          float f[32];
+          } else if (row_ok && col0 < p.N) {
+            const bool full = (col0 + 32 <= p.N);
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
-          if (p.bias) {
+            for (int j = 0; j < 32; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-          }
-          if (rrow) {
-            if (full && vec32) {
+              for (int j = 0; j < 32; ++j)
+                if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+            }
+            if (rrow) {
+              if (full && vec32) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rrow + col0 + j);
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(rrow + col0 + j);
+                  f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) f[j] += rrow[col0 + j];
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += rrow[col0 + j];
             }
-          }
-          if (row_zero) {
+            if (row_zero) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;
-          }
-          if (p.act32) {
-            if (p.act == kActGelu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-            } else if (p.act == kActRelu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
             }
-          }
-          if (p.out32) {
-            float* o = p.out32 + static_cast<size_t>(row) * p.ld32 + col0;
-            if (full && vec32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = f[j];
-            }
-          }
-          if (p.out16) {
             if (p.act32) {
-            } else if (p.act == kActGelu) {
+              if (p.act == kActGelu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-            } else if (p.act == kActRelu) {
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              } else if (p.act == kActRelu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            __half* o = p.out16 + static_cast<size_t>(row) * p.ld16 + col0;
-            if (full && vec16) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
-                __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
-                __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
               }
-            } else {
+            }
+            if (p.out32) {
+              float* o = p.out32 + static_cast<size_t>(row) * p.ld32 + col0;
+              if (full && vec32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = f[j];
+              }
+            }
+            if (p.out16) {
+              if (p.act32) {
+              } else if (p.act == kActGelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              } else if (p.act == kActRelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              __half* o = p.out16 + static_cast<size_t>(row) * p.ld16 + col0;
+              if (full && vec16) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
+                  __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                  __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
+                  __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                  *reinterpret_cast<uint4*>(o + j) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
+              }
             }
           }
         }
+        if (p.argmin_out && it.last_n()) {
+          // merge the two column halves: smaller distance wins, equal distances -> smaller index
+          // (== first minimum over the whole row, as torch.min returns)
+          if (half == 1) { xch_val[q * 32 + lane] = best; xch_idx[q * 32 + lane] = best_idx; }
+          named_bar_sync_64(1 + q);
+          if (half == 0) {
+            const float ob = xch_val[q * 32 + lane];
+            const int oi = xch_idx[q * 32 + lane];
+            if (ob < best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+            if (row_ok) p.argmin_out[row] = best_idx;
+          }
+          named_bar_sync_64(1 + q);
+          best = INFINITY;
+          best_idx = 0;
+        }
+        // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
-      if (p.argmin_out && it.last_n()) {
-        if (row_ok) p.argmin_out[row] = best_idx;
-        best = INFINITY;
-        best_idx = 0;
+    } else {
+      // ---------------------------------------------------------- TMA-store epilogues
+      // chunk = 128 bytes of output per row: 64 fp16 columns (Store16) or 32 fp32 columns (Add32).
+      constexpr int kChunkCols = (EPI == kEpiStore16) ? 64 : 32;
+      constexpr int kChunks = BN / kChunkCols;
+      constexpr int kChunksPerHalf = kChunks / 2;
+      uint8_t* stage_buf = smem + S::kStagingOffset + (warp - 4) * 4096;   // [32 rows][128 B], 128B-swizzled
+      const uint32_t srow = smem_u32(stage_buf) + lane * 128;
+      const int sw = lane & 7;
+      for (TileIter it(tiles_m, tiles_n, false); it.valid(); it.next()) {
+        const int m0 = it.m0(kGemmBM);
+        const int n0 = it.n0(BN);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < kChunksPerHalf; ++cc) {
+          const int c = half * kChunksPerHalf + cc;
+          const int col0 = n0 + c * kChunkCols;
+          uint32_t pk[32];
+          if constexpr (EPI == kEpiStore16) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[32];
+              tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 64 + hh * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col0 + hh * 32 + j < p.N)
+                  b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + hh * 32 + j));
+                float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
+                float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
+                if (p.act == kActGelu) {
+                  f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+                } else if (p.act == kActRelu) {
+                  f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+                }
+                __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+                pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h0);
+                pk[hh * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              }
+            }
+          } else {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias && col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
+              pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
+              pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
+              pk[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b4.w);
+            }
+          }
+          // the previous TMA store of this warp must have finished reading the staging tile
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
+            if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
-      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
+      if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before the CTA exits
     }
   }
 

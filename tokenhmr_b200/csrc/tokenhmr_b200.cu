@@ -348,7 +348,7 @@ int thmr_engine_forward(thmr_engine* e, const float* img, int B, const thmr_outp
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   THMR_TRY(engine_prepare(e, B, workspace, st));
   RunCtx ctx{img, *out, nullptr};
-  for (auto& step : e->steps) THMR_TRY(step(ctx, st));
+  for (auto& step : e->steps) THMR_TRY(step.fn(ctx, st));
   return THMR_OK;
 }
 
@@ -357,8 +357,42 @@ int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* toke
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   THMR_TRY(engine_prepare(e, B, workspace, st));
   RunCtx ctx{img, thmr_outputs{}, tokens};
-  for (size_t i = 0; i < e->vit_steps; ++i) THMR_TRY(e->steps[i](ctx, st));
+  for (size_t i = 0; i < e->vit_steps; ++i) THMR_TRY(e->steps[i].fn(ctx, st));
   return THMR_OK;
+}
+
+int thmr_engine_num_steps(const thmr_engine* e) { return e ? static_cast<int>(e->steps.size()) : 0; }
+
+int thmr_engine_step_info(const thmr_engine* e, int i, const char** name, double* flops, double* bytes) {
+  THMR_CHECK(e && i >= 0 && i < static_cast<int>(e->steps.size()), "step_info: bad index");
+  if (name) *name = e->steps[i].name;
+  if (flops) *flops = e->steps[i].flops;
+  if (bytes) *bytes = e->steps[i].bytes;
+  return THMR_OK;
+}
+
+int thmr_engine_profile(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace, void* stream,
+                        float* step_ms, int cap) {
+  THMR_CHECK(img && out && step_ms, "engine_profile: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  THMR_TRY(engine_prepare(e, B, workspace, st));
+  const int n = static_cast<int>(e->steps.size());
+  THMR_CHECK(cap >= n, "engine_profile: step_ms holds %d entries, need %d", cap, n);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& x : ev) THMR_CUDA(cudaEventCreate(&x));
+  RunCtx ctx{img, *out, nullptr};
+  int status = THMR_OK;
+  THMR_CUDA(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < n && status == THMR_OK; ++i) {
+    status = e->steps[i].fn(ctx, st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (status == THMR_OK && ce == cudaSuccess)
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&step_ms[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (ce != cudaSuccess) return fail(THMR_ERR_CUDA, "engine_profile: %s", cudaGetErrorString(ce));
+  return status;
 }
 
 int thmr_engine_num_launches(const thmr_engine* e) {

@@ -146,6 +146,29 @@ class TokenHMREngine(nn.Module):
         return out
 
     @torch.no_grad()
+    def profile(self, img: torch.Tensor) -> list:
+        """One eager forward with a CUDA event between launch groups.  Returns [(label, ms, flops, bytes), ...]
+        (labels and algorithmic work come from the engine: thmr_engine_step_info)."""
+        B = img.shape[0]
+        with torch.cuda.device(self.device):
+            st = self._state(B, False)
+            st["t"]["img"].copy_(img.to(torch.float32))
+            if not st["warm"]:
+                self._launch(st, B)
+                torch.cuda.current_stream().synchronize()
+                st["warm"] = True
+            n = lib().thmr_engine_num_steps(self._h)
+            ms = (ctypes.c_float * n)()
+            check(lib().thmr_engine_profile(self._h, st["t"]["img"].data_ptr(), B, ctypes.byref(st["outs"]),
+                                            st["ws_ptr"], torch.cuda.current_stream().cuda_stream, ms, n))
+            out = []
+            for i in range(n):
+                name, fl, by = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_double()
+                check(lib().thmr_engine_step_info(self._h, i, ctypes.byref(name), ctypes.byref(fl), ctypes.byref(by)))
+                out.append((name.value.decode(), float(ms[i]), fl.value, by.value))
+            return out
+
+    @torch.no_grad()
     def backbone(self, img: torch.Tensor) -> torch.Tensor:
         """ViT.forward (vit.py:341-343): (B,3,256,256) -> (B,1280,16,12) like the reference backbone."""
         B = img.shape[0]
