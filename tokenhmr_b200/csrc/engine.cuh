@@ -198,6 +198,9 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     GemmPlan plan;
     const int s = gemm_make_plan(d, &plan);
     if (s != THMR_OK) { err = s; return; }
+    S.flops = 2.0 * d.M * d.N * d.K;
+    S.bytes = 0;
+    S.push_back([plan](const RunCtx&, cudaStream_t st) -> int { return gemm_launch(plan, st); });
   };
   auto linear = [&](const __half* A, int lda, int rows, const void* Wt, int N, int K, const float* bias, int act,
                     float* o32, __half* o16, const float* resid = nullptr) {
