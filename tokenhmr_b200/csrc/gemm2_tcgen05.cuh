@@ -1,0 +1,232 @@
+// CTA-pair tcgen05 GEMM (cta_group::2): two CTAs of a cluster compute one 256 x 256 output tile.
+//
+// Why: with one CTA per 128 x 256 tile every k-block moves 48 KB of operands through L2 -> SM for 128*256*64
+// MACs; the profile (profiles/r1_gemm_ncu.md) shows the tensor pipe waiting on that feed.  In a pair each CTA
+// stages its own 128 rows of A plus only HALF of the B tile (128 of the 256 weight rows) and the UMMA reads the
+// other half from the peer's shared memory: 32 KB per k-block per SM for the same MACs, 1.5x less L2 traffic.
+//
+//   both CTAs : warp 0 TMA producer (own A rows, own half of B; bytes credited to the LEADER's full barrier)
+//               warps 4-11 epilogue of the CTA's own 128 accumulator rows (own TMEM)
+//   leader    : warp 1 issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and multicasts the completion to the
+//               "smem slot free" and "accumulator ready" barriers of both CTAs
+//   peer      : its epilogue warps release the accumulator buffer by arriving on the leader's barrier
+//
+// Only the TMA epilogues are supported here (fp16 store, fp32 reduce-add); everything else runs on the
+// single-CTA kernel.  The reduce-add flavour supports split-K (partial tiles add into the output in L2).
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace thmr {
+
+constexpr int kG2BN = 256;
+constexpr int kG2Stages = 6;
+constexpr uint32_t kG2ABytes = kGemmBM * kGemmBK * 2;        // 16 KB: this CTA's 128 rows of A
+constexpr uint32_t kG2BBytes = (kG2BN / 2) * kGemmBK * 2;    // 16 KB: this CTA's half of the B tile
+constexpr uint32_t kG2StageBytes = kG2ABytes + kG2BBytes;
+constexpr uint32_t kG2StagingOffset = kG2Stages * kG2StageBytes;
+constexpr uint32_t kG2BarOffset = kG2StagingOffset + kGemmEpiWarps * 4096;
+constexpr uint32_t kG2SmemTotal = kG2BarOffset + 256 + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int ksplit) {
+  static_assert(EPI == kEpiStore16 || EPI == kEpiAdd32, "2-CTA GEMM supports the TMA epilogues only");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kG2BarOffset);   // used in the leader only
+  uint64_t* empty_bar = full_bar + kG2Stages;
+  uint64_t* tfull_bar = empty_bar + kG2Stages;
+  uint64_t* tempty_bar = tfull_bar + 2;                                     // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int tiles_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int tiles_n = (p.N + kG2BN - 1) / kG2BN;
+  const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
+  const int num_tiles = tiles_m * tiles_n * ksplit;
+
+  if (warp == kWarpTma && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == kWarpMma && lane == 0) {
+    for (int s = 0; s < kG2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * kGemmEpiWarps);   // epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == kWarpAlloc) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // peer barriers initialised, both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kWarpTma) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int ks = tile % ksplit;
+        const int rest = tile / ksplit;
+        const int m0 = (rest / tiles_n) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+        const int n0 = (rest % tiles_n) * kG2BN + static_cast<int>(rank) * (kG2BN / 2);
+        const int kb0 = ks * kb_per;
+        const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kG2StageBytes;
+          uint8_t* sb = sa + kG2ABytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
+          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, m0);
+          tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, n0);
+          if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_f16(2 * kGemmBM, kG2BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int ks = tile % ksplit;
+        const int kb0 = ks * kb_per;
+        const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+        mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kG2BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kG2StageBytes);
+          const uint32_t sb = sa + kG2ABytes;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm_mcast(&empty_bar[stage], 3);
+          if (kb == kb1 - 1) umma_commit_2sm_mcast(&tfull_bar[acc], 3);
+          if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
+        }
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < kGemmEpiWarps) {
+    // -------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    constexpr int kChunkCols = (EPI == kEpiStore16) ? 64 : 32;
+    constexpr int kChunksPerHalf = kG2BN / kChunkCols / 2;
+    uint8_t* stage_buf = smem + kG2StagingOffset + warp * 4096;
+    const uint32_t srow = smem_u32(stage_buf) + lane * 128;
+    const int sw = lane & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int ks = tile % ksplit;
+      const int rest = tile / ksplit;
+      const int m0 = (rest / tiles_n) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+      const int n0 = (rest % tiles_n) * kG2BN;
+      const bool add_bias = p.bias && ks == 0;
+      mbar_wait_cluster(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < ((p.dbg & 1) ? 0 : kChunksPerHalf); ++cc) {
+        const int c = half * kChunksPerHalf + cc;
+        const int col0 = n0 + c * kChunkCols;
+        uint32_t pk[32];
+        if constexpr (EPI == kEpiStore16) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_base + lane_addr + acc * kG2BN + c * 64 + hh * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add_bias && col0 + hh * 32 + j < p.N)
+                b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + hh * 32 + j));
+              float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
+              float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
+              if (p.act == kActGelu) {
+                f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
+              } else if (p.act == kActRelu) {
+                f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+              }
+              __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+              pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[hh * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_base + lane_addr + acc * kG2BN + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias && col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
+            pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
+            pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
+            pk[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b4.w);
+          }
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
+          if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+          else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // accumulator buffer free (leader's barrier)
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // neither CTA may exit (or free TMEM) while the peer can still reach it
+  if (warp == kWarpAlloc) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+}  // namespace thmr

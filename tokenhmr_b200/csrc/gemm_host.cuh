@@ -1,6 +1,9 @@
 // Host side of the tcgen05 GEMM: plan construction (TMA descriptors, tile choice) and launch.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
+
+#include "gemm2_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace thmr {
@@ -11,6 +14,8 @@ struct GemmPlan {
   int bn;
   int epi;
   int grid;
+  int two_cta;  // CTA-pair kernel (256 x 256 tiles)
+  int ksplit;   // split-K factor (reduce-add epilogue only)
 };
 
 struct GemmDesc {
@@ -29,6 +34,7 @@ struct GemmDesc {
   long long* argmin_out = nullptr; const float* row_sq = nullptr; const float* col_sq = nullptr;
   int force_bn = 0;
   int force_epi = -1;  // 0 forces the generic epilogue (tests)
+  int force_2cta = -1; // -1 auto, 0 never, 1 always (when eligible)
 };
 
 // Which epilogue can serve this GEMM (see gemm_tcgen05.cuh).
@@ -69,8 +75,9 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_CHECK(d.out32 || d.out16 || d.argmin_out, "gemm: no output");
   int epi = pick_epi(d);
   if (d.force_bn && d.force_bn < 128) epi = kEpiGeneric;
+  THMR_CHECK(d.force_bn != 512 || epi != kEpiGeneric, "gemm: block_n 512 (CTA pair) needs a TMA-epilogue eligible call");
   if (d.force_epi >= 0) epi = d.force_epi == kEpiGeneric ? kEpiGeneric : epi;
-  const int bn = pick_bn(d.M, d.N, d.force_bn, epi);
+  const int bn = pick_bn(d.M, d.N, d.force_bn == 512 ? 0 : d.force_bn, epi);
   THMR_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm: bad block_n %d", bn);
   GemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -78,6 +85,8 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   p.out32 = d.out32; p.ld32 = d.ld32; p.out16 = d.out16; p.ld16 = d.ld16;
   p.bias = d.bias; p.resid = d.resid; p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.act = d.act; p.act32 = d.act32;
   p.seq_pitch = d.seq_pitch; p.seq_lo = d.seq_lo; p.seq_hi = d.seq_hi;
+  { const char* e = getenv("THMR_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("THMR_GEMM_COUNTERS"); p.dbg_counters = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   p.alpha = d.alpha; p.argmin_out = d.argmin_out; p.row_sq = d.row_sq; p.col_sq = d.col_sq;
   const int num_kb = (d.K + kGemmBK - 1) / kGemmBK;
   uint64_t a_cols = d.K;
@@ -89,9 +98,17 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   } else {
     p.kblocks_per_tap = num_kb;
   }
+  // CTA-pair kernel for the large TMA-epilogue GEMMs (the ViT projections): env THMR_GEMM_2CTA=0 disables it
+  static const int env_2cta = [] { const char* e = getenv("THMR_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  bool two = epi != kEpiGeneric && d.taps == 1 && d.M >= 256 && d.N >= 256 && !d.force_bn && env_2cta != 0;
+  if (d.force_2cta == 0) two = false;
+  if (d.force_2cta == 1 || d.force_bn == 512) two = epi != kEpiGeneric && d.taps == 1;
+  plan->two_cta = two ? 1 : 0;
+  plan->ksplit = 1;
   THMR_TRY(make_tmap_2d_f16(&plan->tmA, d.A, d.a_rows, a_cols, d.lda, kGemmBM, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
-  THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, bn, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
-  plan->bn = bn;
+  const int b_box_rows = two ? kG2BN / 2 : bn;
+  THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, b_box_rows, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  plan->bn = two ? kG2BN : bn;
   plan->epi = epi;
   if (epi == kEpiStore16)
     THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, 32, 64,
@@ -101,6 +118,23 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
                           CU_TENSOR_MAP_SWIZZLE_128B));
   else
     plan->tmC = plan->tmA;
+  if (two) {
+    const int clusters = num_sms() / 2;
+    const long tiles = static_cast<long>((d.M + 255) / 256) * ((d.N + kG2BN - 1) / kG2BN);
+    if (epi == kEpiAdd32) {
+      // split-K when the tile count quantises badly over the 74 CTA pairs (partials reduce-add in L2)
+      double best_eff = 0;
+      for (int ks = 1; ks <= 4; ks *= 2) {
+        if (ks > 1 && num_kb / ks < 16) break;
+        const long t = tiles * ks;
+        const double eff = static_cast<double>(t) / (((t + clusters - 1) / clusters) * clusters);
+        if (eff > best_eff + 0.05) { best_eff = eff; plan->ksplit = ks; }
+      }
+    }
+    const long t = tiles * plan->ksplit;
+    plan->grid = 2 * static_cast<int>(t < clusters ? t : clusters);
+    return THMR_OK;
+  }
   const long tiles_m = (d.M + kGemmBM - 1) / kGemmBM;
   const long tiles = d.argmin_out ? tiles_m : tiles_m * ((d.N + bn - 1) / bn);
   plan->grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
@@ -122,7 +156,26 @@ inline int gemm_launch_t(const GemmPlan& plan, cudaStream_t stream) {
   return THMR_OK;
 }
 
+template <int EPI>
+inline int gemm2_launch_t(const GemmPlan& plan, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    THMR_CUDA(cudaFuncSetAttribute(gemm_f16_tn_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kG2SmemTotal));
+    configured = true;
+  }
+  gemm_f16_tn_2cta_kernel<EPI><<<plan.grid, kGemmThreads, kG2SmemTotal, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p,
+                                                                                  plan.ksplit);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
 inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.two_cta) {
+    if (plan.epi == kEpiStore16) return gemm2_launch_t<kEpiStore16>(plan, stream);
+    if (plan.epi == kEpiAdd32) return gemm2_launch_t<kEpiAdd32>(plan, stream);
+    return fail(THMR_ERR_INVALID, "gemm: CTA-pair kernel needs a TMA epilogue");
+  }
   if (plan.epi == kEpiStore16) {
     if (plan.bn == 256) return gemm_launch_t<256, 4, kEpiStore16>(plan, stream);
     if (plan.bn == 128) return gemm_launch_t<128, 6, kEpiStore16>(plan, stream);

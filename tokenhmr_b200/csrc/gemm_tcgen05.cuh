@@ -2,10 +2,10 @@
 //   A (activations) and B (nn.Linear / conv weight, stored [out, in]) are both K-major fp16,
 //   accumulation is fp32 in TMEM.
 //
-//   warp 0     : TMA producer (one thread)       global -> 128B-swizzled smem ring
-//   warp 1     : MMA issuer   (one thread)       tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
-//   warp 2     : TMEM allocator / deallocator
-//   warps 4-11 : epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns)
+//   warps 0-7  : epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns)
+//   warp 8     : TMA producer (one thread)       global -> 128B-swizzled smem ring
+//   warp 9     : MMA issuer   (one thread)       tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 10    : TMEM allocator / deallocator
 //
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 //
@@ -49,6 +49,8 @@ struct GemmParams {
   long long* argmin_out;   // [M] int64 (nullable = normal GEMM)
   const float* row_sq;     // [M]
   const float* col_sq;     // [N]
+  unsigned long long* dbg_counters;  // optional [gridDim.x][8] cycle counters (scripts/dev_gemm_qkv.py)
+  int dbg;                 // THMR_GEMM_DBG experiments: 1 = skip epilogue work, 2 = skip only the TMA store
 };
 
 // Tile order shared by the three warp roles.  Normal mode: tiles round-robin over CTAs, column tile
@@ -78,7 +80,12 @@ struct TileIter {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmEpiWarps = 8;
-constexpr int kGemmThreads = 128 + 32 * kGemmEpiWarps;  // 4 control warps + 8 epilogue warps
+constexpr int kGemmThreads = 128 + 32 * kGemmEpiWarps;  // 8 epilogue warps + 4 control warps
+// The SMSP arbiter favours the highest warp id: the latency-critical single-thread roles get the top ids so that
+// bursts of epilogue ALU work (bias, GELU, packing) never delay a TMA issue or a tcgen05.mma issue.
+constexpr int kWarpTma = kGemmEpiWarps;        // 8
+constexpr int kWarpMma = kGemmEpiWarps + 1;    // 9
+constexpr int kWarpAlloc = kGemmEpiWarps + 2;  // 10
 
 template <int BN, int STAGES, int EPI>
 struct GemmSmem {
@@ -129,12 +136,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != kEpiGeneric) tma_prefetch_desc(&tmC);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -145,7 +152,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -154,16 +161,20 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
         for (int kb = 0; kb < num_kb; ++kb) {
+          const long long t0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          w_empty += clock64() - t0;
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           const int tap = kb / p.kblocks_per_tap;
@@ -174,8 +185,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg_counters) {
+        p.dbg_counters[blockIdx.x * 8 + 0] = w_empty;
+        p.dbg_counters[blockIdx.x * 8 + 1] = clock64() - t_begin;
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(kGemmBM, BN);
@@ -183,12 +198,18 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+        long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        w_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          t0 = clock64();
           mbar_wait(&full_bar[stage], phase);
+          w_full += clock64() - t0;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
@@ -204,11 +225,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
+      if (p.dbg_counters) {
+        p.dbg_counters[blockIdx.x * 8 + 2] = w_tempty;
+        p.dbg_counters[blockIdx.x * 8 + 3] = w_full;
+        p.dbg_counters[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      }
     }
-  } else if (warp >= 4) {
+  } else if (warp < kGemmEpiWarps) {
     // -------------------------------------------------------------- epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the tile's columns
+    const int half = warp >> 2;  // which half of the tile's columns
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -362,29 +388,39 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       constexpr int kChunkCols = (EPI == kEpiStore16) ? 64 : 32;
       constexpr int kChunks = BN / kChunkCols;
       constexpr int kChunksPerHalf = kChunks / 2;
-      uint8_t* stage_buf = smem + S::kStagingOffset + (warp - 4) * 4096;   // [32 rows][128 B], 128B-swizzled
+      uint8_t* stage_buf = smem + S::kStagingOffset + warp * 4096;   // [32 rows][128 B], 128B-swizzled
       const uint32_t srow = smem_u32(stage_buf) + lane * 128;
       const int sw = lane & 7;
+      long long w_tfull = 0;
+      const long long t_begin = clock64();
       for (TileIter it(tiles_m, tiles_n, false); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
+        const long long t0 = clock64();
         mbar_wait(&tfull_bar[acc], acc_phase);
+        w_tfull += clock64() - t0;
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < kChunksPerHalf; ++cc) {
-          const int c = half * kChunksPerHalf + cc;
+        const int my_chunks = (p.dbg & 1) ? 0 : ((p.dbg & 4) ? (half == 0 ? kChunks : 0) : kChunksPerHalf);
+        for (int cc = 0; cc < my_chunks; ++cc) {
+          const int c = ((p.dbg & 4) ? 0 : half * kChunksPerHalf) + cc;
           const int col0 = n0 + c * kChunkCols;
           uint32_t pk[32];
           if constexpr (EPI == kEpiStore16) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t v[32];
-              tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 64 + hh * 32, v);
-              tmem_ld_wait();
+              if (!(p.dbg & 32)) {
+                tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 64 + hh * 32, v);
+                tmem_ld_wait();
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = j + lane;
+              }
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && col0 + hh * 32 + j < p.N)
+                if (p.bias && !(p.dbg & 8) && col0 + hh * 32 + j < p.N)
                   b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + hh * 32 + j));
                 float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
                 float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
@@ -415,15 +451,19 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           // the previous TMA store of this warp must have finished reading the staging tile
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+          if (!(p.dbg & 16)) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
-                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                         : "memory");
+            for (int j = 0; j < 8; ++j) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+            }
+            if (!(p.dbg & 64)) fence_proxy_async_smem();
+          } else if (pk[0] == 0x12345678u && pk[31] == 0x9abcdef0u) {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(srow), "r"(pk[7]) : "memory");
           }
-          fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M) {
+          if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
             if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
             else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
             tma_store_commit();
@@ -434,13 +474,17 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
+      if (p.dbg_counters && warp == 0 && lane == 0) {
+        p.dbg_counters[blockIdx.x * 8 + 5] = w_tfull;
+        p.dbg_counters[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      }
       if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before the CTA exits
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
