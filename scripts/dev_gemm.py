@@ -43,7 +43,7 @@ for (M, N, K) in [(128, 256, 64), (300, 520, 200), (1024, 1280, 5120), (64, 1024
         gemm(A, B, bias, x, 0, x, None, bn)
         ec = ((x - (r + resid)).abs().max() / (r + resid).abs().max()).item()
         rc = L.thmr_check_device_flags()
-        report(f"M={M} N={N} K={K} bn={bn}", e32 < 1e-5 and e16 < 2e-3 and e16b < 2e-3 and ec < 1e-5 and rc == 0,
+        report(f"M={M} N={N} K={K} bn={bn}", e32 < 2e-5 and e16 < 2e-3 and e16b < 2e-3 and ec < 2e-5 and rc == 0,
                f"gen32={e32:.1e} gen16={e16:.1e} store16={e16b:.1e} add32={ec:.1e} flags={rc}")
         if rc != 0: print(L.thmr_last_error()); sys.exit(1)
 print("CORRECTNESS", "PASS" if ok else "FAIL", flush=True)

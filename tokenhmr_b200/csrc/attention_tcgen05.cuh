@@ -12,6 +12,8 @@
 //   warp 1      MMA issuer, TMEM owner (512 columns: S tile t at columns [192 t, 192 t + 192), O_t aliases S_t)
 //   warps 2..9  softmax + epilogue: thread = one query row x 96 of the 192 key columns
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -37,6 +39,7 @@ struct AttnParams {
   __half* out;       // [B*192, ldo], head h at columns [80 h, 80 h + 80)
   int ldo;
   float* dbg_s;      // optional [B*H, 192, 192] raw scores (tests only)
+  unsigned long long* dbg_counters;  // optional [gridDim.x][16] cycle counters (THMR_ATTN_COUNTERS)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -119,13 +122,19 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAttTokens);            // Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc_f16(128, kAttHeadDim, 0, 1);     // P V   : V is N-major (d contiguous)
       int i = 0;
+      long long w_qk = 0, w_oe = 0, w_v = 0, w_p = 0;
+      const long long t_begin = clock64();
       for (int prob = blockIdx.x; prob < p.num_problems; prob += gridDim.x, ++i) {
         const int buf = i & 1;
         const uint32_t sQ = smem_u32(smem + kAttOffQK + buf * 2 * kAttMatBytes);
         const uint32_t sK = sQ + kAttMatBytes;
+        long long t0 = clock64();
         mbar_wait(&qk_full[buf], (i >> 1) & 1);
+        w_qk += clock64() - t0;
         for (int t = 0; t < 2; ++t) {
+          t0 = clock64();
           mbar_wait(&o_empty[t], (i & 1) ^ 1);   // epilogue of the previous head has drained O_t (aliases S_t)
+          w_oe += clock64() - t0;
           tc_fence_after();
 #pragma unroll
           for (int kc = 0; kc < kAttChunks; ++kc) {
@@ -136,10 +145,14 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
           umma_commit(&s_full[t]);
         }
         umma_commit(&qk_empty[buf]);
+        t0 = clock64();
         mbar_wait(v_full, i & 1);
+        w_v += clock64() - t0;
         const uint32_t sPa = smem_u32(sP), sVa = smem_u32(sV);
         for (int t = 0; t < 2; ++t) {
+          t0 = clock64();
           mbar_wait(p_full, t);                  // completion #(2i + t)
+          w_p += clock64() - t0;
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < kAttTokens / 16; ++ks) {
@@ -152,6 +165,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
         }
         umma_commit(v_empty);
       }
+      if (p.dbg_counters) {
+        unsigned long long* c = p.dbg_counters + blockIdx.x * 16;
+        c[0] = w_qk; c[1] = w_oe; c[2] = w_v; c[3] = w_p; c[4] = clock64() - t_begin;
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
@@ -160,11 +177,15 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
     const int trow = q * 32 + lane;      // row inside the 128-row tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     int i = 0;
+    long long w_s = 0, w_pe = 0, w_of = 0, w_bar = 0;
+    const long long t_begin = clock64();
     for (int prob = blockIdx.x; prob < p.num_problems; prob += gridDim.x, ++i) {
       const int b = prob / p.heads, h = prob % p.heads;
       for (int t = 0; t < 2; ++t) {
         const bool active = (t == 0) || (q >= 2);
+        long long t0 = clock64();
         mbar_wait(&s_full[t], i & 1);
+        w_s += clock64() - t0;
         tc_fence_after();
         uint32_t pk[48];
         float sum = 0.f;
@@ -189,7 +210,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
 #pragma unroll
           for (int e = 1; e < 96; ++e) m = fmaxf(m, s[e]);
           smax[(t * 2 + half) * 128 + trow] = m;
+          t0 = clock64();
           named_bar_sync(1 + q, 64);
+          w_bar += clock64() - t0;
           m = fmaxf(m, smax[(t * 2 + (half ^ 1)) * 128 + trow]);
           const float mo = m * p.scale_log2e;
 #pragma unroll
@@ -202,7 +225,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
           }
           ssum[(t * 2 + half) * 128 + trow] = sum;
         }
+        t0 = clock64();
         mbar_wait(p_empty, t ^ 1);       // PV of the previous tile has finished reading P
+        w_pe += clock64() - t0;
         if (active) {
           const uint32_t rbase = smem_u32(sP) + (trow >> 3) * 1024 + (trow & 7) * 128;
 #pragma unroll
@@ -221,7 +246,9 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
       }
       for (int t = 0; t < 2; ++t) {
         const bool active = (t == 0) || (q >= 2);
+        const long long t0 = clock64();
         mbar_wait(&o_full[t], i & 1);
+        w_of += clock64() - t0;
         tc_fence_after();
         if (active) {
           const float inv = 1.0f / (ssum[(t * 2) * 128 + trow] + ssum[(t * 2 + 1) * 128 + trow]);
@@ -250,6 +277,10 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[t]);
       }
+    }
+    if (p.dbg_counters && warp == 4 && lane == 0) {
+      unsigned long long* c = p.dbg_counters + blockIdx.x * 16;
+      c[8] = w_s; c[9] = w_pe; c[10] = w_of; c[11] = w_bar; c[12] = clock64() - t_begin;
     }
   }
 
@@ -295,6 +326,7 @@ inline int attention_make_plan(const __half* qkv, int ld_qkv, int B, int heads, 
   plan->p.out = out;
   plan->p.ldo = ldo;
   plan->p.dbg_s = dbg_s;
+  { const char* e = getenv("THMR_ATTN_COUNTERS"); plan->p.dbg_counters = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   plan->grid = plan->p.num_problems < num_sms() ? plan->p.num_problems : num_sms();
   return THMR_OK;
 }

@@ -83,6 +83,8 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       // ------------------------------------------------------------ TMA producer (both CTAs)
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int ks = tile % ksplit;
         const int rest = tile / ksplit;
@@ -91,7 +93,9 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int kb0 = ks * kb_per;
         const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long t0 = clock64();
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          w_empty += clock64() - t0;
           uint8_t* sa = smem + stage * kG2StageBytes;
           uint8_t* sb = sa + kG2ABytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
@@ -99,6 +103,10 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (p.dbg_counters) {
+        p.dbg_counters[blockIdx.x * 8 + 0] = w_empty;
+        p.dbg_counters[blockIdx.x * 8 + 1] = clock64() - t_begin;
       }
     }
   } else if (warp == kWarpMma) {
@@ -109,29 +117,47 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_begin = clock64();
+      bool ready = false;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int ks = tile % ksplit;
         const int kb0 = ks * kb_per;
         const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+        long long t0 = clock64();
         mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        w_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kG2BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
+          if (!ready) {
+            t0 = clock64();
+            mbar_wait_cluster(&full_bar[stage], phase);
+            w_full += clock64() - t0;
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kG2StageBytes);
           const uint32_t sb = sa + kG2ABytes;
+          const int nstage = (stage + 1 == kG2Stages) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == kG2Stages) ? (phase ^ 1) : phase;
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
             const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
             umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (k == 1) ready = mbar_try_wait_cluster(&full_bar[nstage], nphase);   // peek the next stage
           }
           umma_commit_2sm_mcast(&empty_bar[stage], 3);
           if (kb == kb1 - 1) umma_commit_2sm_mcast(&tfull_bar[acc], 3);
-          if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+      if (p.dbg_counters) {
+        p.dbg_counters[blockIdx.x * 8 + 2] = w_tempty;
+        p.dbg_counters[blockIdx.x * 8 + 3] = w_full;
+        p.dbg_counters[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
     }
   } else if (warp < kGemmEpiWarps) {
@@ -152,7 +178,14 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int m0 = (rest / tiles_n) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
       const int n0 = (rest % tiles_n) * kG2BN;
       const bool add_bias = p.bias && ks == 0;
-      mbar_wait_cluster(&tfull_bar[acc], acc_phase);
+      // this warp's 128 bias values (lane l: columns 4l..4l+3 of its column half), fetched while the MMAs run
+      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int bc = n0 + half * (kG2BN / 2) + lane * 4;
+        if (add_bias && lane * 4 < kG2BN / 2 && bc < p.N) bq = __ldg(reinterpret_cast<const float4*>(p.bias + bc));
+      }
+      if (lane == 0) mbar_wait_cluster(&tfull_bar[acc], acc_phase);   // one polling lane per warp
+      __syncwarp();
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < ((p.dbg & 1) ? 0 : kChunksPerHalf); ++cc) {
@@ -167,9 +200,10 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (add_bias && col0 + hh * 32 + j < p.N)
-                b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + hh * 32 + j));
+              const int bl = (cc * 64 + hh * 32 + j) >> 2;   // lane holding these 4 columns' bias
+              float4 b4;
+              b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
+              b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
               float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
               float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
               if (p.act == kActGelu) {
@@ -188,8 +222,10 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (add_bias && col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            const int bl = (cc * 32 + j) >> 2;
+            float4 b4;
+            b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
+            b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
             pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
             pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
             pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);

@@ -98,7 +98,23 @@ struct GemmSmem {
   static constexpr uint32_t kTotal = kBarOffset + 1280 + 1024;  // barriers + argmin exchange, alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU default, vit.py:73).  The epilogue evaluates 63 M of these per MLP layer, so erf uses
+// Abramowitz-Stegun 7.1.28  erf(a) = 1 - (1 + c1 a + ... + c6 a^6)^-16  (|err| < 2e-6 in fp32, i.e. GELU within
+// 9e-7 absolute of the libm path; the result is rounded to fp16 afterwards): 7 FMA + 4 MUL + 1 MUFU.RCP, no branches.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = fabsf(x) * 0.70710678118654752f;
+  float p = fmaf(0.0000430638f, a, 0.0002765672f);
+  p = fmaf(p, a, 0.0001520143f);
+  p = fmaf(p, a, 0.0092705272f);
+  p = fmaf(p, a, 0.0422820123f);
+  p = fmaf(p, a, 0.0705230784f);
+  p = fmaf(p, a, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));   // 1 ulp-class MUFU reciprocal (p >= 1; p = inf -> 0)
+  const float e = 1.0f - r;                       // erf(|x| / sqrt(2))
+  return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) e)
+}
 
 __device__ __forceinline__ void named_bar_sync_64(int id) {
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
@@ -200,6 +216,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t acc_phase = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
+      // The readiness of the NEXT smem stage is polled between the MMA issues of the current one, so the
+      // latency of mbarrier.try_wait (~100-200 cycles even when the phase is complete) overlaps with tensor work
+      // instead of sitting between two k-blocks.
+      bool ready = false;
       for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
         long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -207,21 +227,27 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          t0 = clock64();
-          mbar_wait(&full_bar[stage], phase);
-          w_full += clock64() - t0;
+          if (!ready) {
+            t0 = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            w_full += clock64() - t0;
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kABytes;
+          const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+          const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
             const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
             umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (k == 1) ready = mbar_try_wait(&full_bar[nstage], nphase);   // peek (result is only a hint)
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
@@ -259,7 +285,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const float* rrow = nullptr;
         if (p.resid) rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldr;
 
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one polling lane per warp
+        __syncwarp();
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < kChunksPerHalf; ++cc) {
@@ -391,19 +418,26 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint8_t* stage_buf = smem + S::kStagingOffset + warp * 4096;   // [32 rows][128 B], 128B-swizzled
       const uint32_t srow = smem_u32(stage_buf) + lane * 128;
       const int sw = lane & 7;
-      long long w_tfull = 0;
+      long long w_tfull = 0, w_store = 0;
       const long long t_begin = clock64();
       for (TileIter it(tiles_m, tiles_n, false); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
+        // this warp's BN/2 bias values (lane l: columns 4l..4l+3 of its column half), fetched while the MMAs run
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+          const int bc = n0 + half * (BN / 2) + lane * 4;
+          if (p.bias && !(p.dbg & 8) && lane * 4 < BN / 2 && bc < p.N) bq = __ldg(reinterpret_cast<const float4*>(p.bias + bc));
+        }
         const long long t0 = clock64();
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one polling lane per warp
+        __syncwarp();
         w_tfull += clock64() - t0;
         tc_fence_after();
 #pragma unroll 1
-        const int my_chunks = (p.dbg & 1) ? 0 : ((p.dbg & 4) ? (half == 0 ? kChunks : 0) : kChunksPerHalf);
+        const int my_chunks = (p.dbg & 1) ? 0 : kChunksPerHalf;
         for (int cc = 0; cc < my_chunks; ++cc) {
-          const int c = ((p.dbg & 4) ? 0 : half * kChunksPerHalf) + cc;
+          const int c = half * kChunksPerHalf + cc;
           const int col0 = n0 + c * kChunkCols;
           uint32_t pk[32];
           if constexpr (EPI == kEpiStore16) {
@@ -419,9 +453,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               }
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && !(p.dbg & 8) && col0 + hh * 32 + j < p.N)
-                  b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + hh * 32 + j));
+                const int bl = (cc * 64 + hh * 32 + j) >> 2;   // lane holding these 4 columns' bias
+                float4 b4;
+                b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
+                b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
                 float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
                 float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
                 if (p.act == kActGelu) {
@@ -440,8 +475,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias && col0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              const int bl = (cc * 32 + j) >> 2;
+              float4 b4;
+              b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
+              b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
               pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
               pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
               pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
@@ -449,8 +486,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           // the previous TMA store of this warp must have finished reading the staging tile
+          const long long tw0 = clock64();
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+          w_store += clock64() - tw0;
           if (!(p.dbg & 16)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -477,6 +516,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (p.dbg_counters && warp == 0 && lane == 0) {
         p.dbg_counters[blockIdx.x * 8 + 5] = w_tfull;
         p.dbg_counters[blockIdx.x * 8 + 6] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 8 + 7] = w_store;
       }
       if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before the CTA exits
     }
