@@ -62,7 +62,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
+
+    def window(self, t0: float, t1: float):
+        self.rows = [r[1:] for r in self.rows if t0 <= r[0] <= t1 + 0.15]
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -82,15 +85,36 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_forward_rate(sample_images: int, repeats: int, threads: int):
+def pick_cpu_threads(sd, smpl, cfg) -> int:
+    """128 torch threads on 1.5 k-row GEMMs is slower than 32 (oversubscription): time one ViT-block-sized
+    matmul at a few thread counts and keep the fastest, so the CPU baseline is the best the host can do."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    x = torch.randn(4 * 192, 1280)
+    w = sd["backbone.blocks.0.mlp.fc1.weight"]
+    best, best_t = ncpu, None
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(n)
+        torch.nn.functional.linear(x, w)
+        t = time.perf_counter()
+        for _ in range(5):
+            torch.nn.functional.linear(x, w)
+        dt = time.perf_counter() - t
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    return best
+
+
+def cpu_forward_rate(sample_images: int, repeats: int):
     """The oracle (fp32 CPU restatement of the reference forward) timed on the host cores."""
     import torch
     from oracle import tokenhmr_oracle as O
     from tokenhmr_b200 import synth
     from tokenhmr_b200.config import release_config
-    torch.set_num_threads(threads)
     cfg = release_config()
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    threads = pick_cpu_threads(sd, smpl, cfg)
+    torch.set_num_threads(threads)
     img = synth.make_images(sample_images, cfg)
     times = []
     with torch.no_grad():
@@ -98,7 +122,7 @@ def cpu_forward_rate(sample_images: int, repeats: int, threads: int):
             t = time.perf_counter()
             O.forward(sd, smpl, img, cfg)
             times.append(time.perf_counter() - t)
-    return sample_images / min(times), times
+    return sample_images / min(times), times, threads
 
 
 def run_reference(args):
@@ -109,14 +133,14 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
     sample = 4                                   # images per step: a bounded sample of the bs=64 workload
     from oracle import tokenhmr_oracle as O
     from tokenhmr_b200 import synth
     from tokenhmr_b200.config import release_config
-    torch.set_num_threads(threads)
     cfg = release_config()
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    threads = pick_cpu_threads(sd, smpl, cfg)
+    torch.set_num_threads(threads)
     img = synth.make_images(sample, cfg)
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -133,7 +157,7 @@ def run_reference(args):
         "config": {"workload": "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)",
                    "sample": f"{sample} images per step"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} images/step x {args.steps} steps, fp32 eager torch, all host threads"},
+                         "sample": f"{sample} images/step x {args.steps} steps, fp32 eager torch, best of 8/16/32/64/all host threads ({os.cpu_count()} available)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -142,7 +166,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,20 +214,26 @@ def main():
         out = model({"img": img_dev})
         return sharded.all_gather(out) if world > 1 else out
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # started early: nvidia-smi needs ~0.5 s before its first sample
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_win0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_resident()
     e1.record()
     barrier()
+    t_win1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        time.sleep(0.12)
+        sampler.window(t_win0, t_win1)
+        clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = world * B * 1e3 / ms_step
 
@@ -259,10 +289,10 @@ def main():
     # ---- (4) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, times = cpu_forward_rate(sample_images=8, repeats=2, threads=threads)
+        v, times, threads = cpu_forward_rate(sample_images=4, repeats=2)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"8 of the 64 images, best of 2 fp32 eager-torch forwards of the oracle ({min(times):.1f}s)"}
+               "sample": f"4 of the 64 images, best of 2 fp32 eager-torch forwards of the oracle ({min(times):.1f}s), "
+                         f"thread count picked from 8/16/32/64/{os.cpu_count()}"}
 
     if rank == 0:
         print(json.dumps({

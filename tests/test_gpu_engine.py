@@ -113,7 +113,11 @@ def test_batch_independence(tiny):
     img = synth.make_images(4, cfg, seed=3)
     full = model({"img": img})["pred_vertices"].clone()
     one = model({"img": img[2:3]})["pred_vertices"]
-    assert torch.equal(full[2:3], one)
+    # not bit-equal: M = 768 rows runs the CTA-pair GEMM tiles, M = 192 the single-CTA ones (different fp32
+    # summation order); the values agree to accumulation noise
+    assert rel_err(one, full[2:3]) < 1e-3
+    again = model({"img": img})["pred_vertices"]
+    assert torch.equal(again, full)          # same shape, same kernels: bit-reproducible run to run
 
 
 def test_release_forward_vs_reference_golden(cuda_dev, golden_dir):

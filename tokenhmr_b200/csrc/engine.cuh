@@ -298,7 +298,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
       const int ld = L * 2 * inner, koff = l * 2 * inner, voff = koff + inner, heads = c.dec_heads;
       const float scale = 1.0f / sqrtf(static_cast<float>(c.dec_dim_head));
       S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
-        dec_cross_attn_kernel<192><<<B, 32 * heads, 0, st>>>(q32, kv, ld, koff, voff, scale, att16, heads);
+        dec_cross_attn_kernel<192><<<B * heads, 192, 0, st>>>(q32, kv, ld, koff, voff, scale, att16, heads);
         THMR_CUDA(cudaGetLastError());
         return THMR_OK;
       });

@@ -105,8 +105,8 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
       if (p.dbg_counters) {
-        p.dbg_counters[blockIdx.x * 8 + 0] = w_empty;
-        p.dbg_counters[blockIdx.x * 8 + 1] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 16 + 0] = w_empty;
+        p.dbg_counters[blockIdx.x * 16 + 1] = clock64() - t_begin;
       }
     }
   } else if (warp == kWarpMma) {
@@ -155,9 +155,9 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
       if (p.dbg_counters) {
-        p.dbg_counters[blockIdx.x * 8 + 2] = w_tempty;
-        p.dbg_counters[blockIdx.x * 8 + 3] = w_full;
-        p.dbg_counters[blockIdx.x * 8 + 4] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 16 + 2] = w_tempty;
+        p.dbg_counters[blockIdx.x * 16 + 3] = w_full;
+        p.dbg_counters[blockIdx.x * 16 + 4] = clock64() - t_begin;
       }
     }
   } else if (warp < kGemmEpiWarps) {
@@ -198,22 +198,29 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             uint32_t v[32];
             tmem_ld_x32(tmem_base + lane_addr + acc * kG2BN + c * 64 + hh * 32, v);
             tmem_ld_wait();
+            float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int bl = (cc * 64 + hh * 32 + j) >> 2;   // lane holding these 4 columns' bias
               float4 b4;
               b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
               b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
-              float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
-              float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
-              if (p.act == kActGelu) {
-                f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
-              } else if (p.act == kActRelu) {
-                f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
-              }
-              __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
-              pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h0);
-              pk[hh * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            // warp-uniform branch OUTSIDE the element loop (otherwise the compiler if-converts it and every element
+            // pays for GELU and ReLU even when no activation is requested)
+            if (p.act == kActGelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == kActRelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              __half2 h2 = __floats2half2_rn(f[j], f[j + 1]);
+              pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h2);
             }
           }
         } else {

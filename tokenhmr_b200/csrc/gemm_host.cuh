@@ -121,8 +121,11 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   if (two) {
     const int clusters = num_sms() / 2;
     const long tiles = static_cast<long>((d.M + 255) / 256) * ((d.N + kG2BN - 1) / kG2BN);
-    if (epi == kEpiAdd32) {
-      // split-K when the tile count quantises badly over the 74 CTA pairs (partials reduce-add in L2)
+    // Split-K makes two partial tiles reduce-add into the same output element in arbitrary order: faster when
+    // the tile count quantises badly over the 74 CTA pairs (fc2: +5 %), but not bit-reproducible run to run,
+    // so it is opt-in (THMR_GEMM_SPLITK=1).
+    static const int env_splitk = [] { const char* e = getenv("THMR_GEMM_SPLITK"); return e ? atoi(e) : 0; }();
+    if (epi == kEpiAdd32 && env_splitk) {
       double best_eff = 0;
       for (int ks = 1; ks <= 4; ks *= 2) {
         if (ks > 1 && num_kb / ks < 16) break;

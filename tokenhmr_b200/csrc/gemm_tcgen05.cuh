@@ -202,8 +202,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
       if (p.dbg_counters) {
-        p.dbg_counters[blockIdx.x * 8 + 0] = w_empty;
-        p.dbg_counters[blockIdx.x * 8 + 1] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 16 + 0] = w_empty;
+        p.dbg_counters[blockIdx.x * 16 + 1] = clock64() - t_begin;
       }
     }
   } else if (warp == kWarpMma) {
@@ -252,9 +252,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
       if (p.dbg_counters) {
-        p.dbg_counters[blockIdx.x * 8 + 2] = w_tempty;
-        p.dbg_counters[blockIdx.x * 8 + 3] = w_full;
-        p.dbg_counters[blockIdx.x * 8 + 4] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 16 + 2] = w_tempty;
+        p.dbg_counters[blockIdx.x * 16 + 3] = w_full;
+        p.dbg_counters[blockIdx.x * 16 + 4] = clock64() - t_begin;
       }
     }
   } else if (warp < kGemmEpiWarps) {
@@ -418,7 +418,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint8_t* stage_buf = smem + S::kStagingOffset + warp * 4096;   // [32 rows][128 B], 128B-swizzled
       const uint32_t srow = smem_u32(stage_buf) + lane * 128;
       const int sw = lane & 7;
-      long long w_tfull = 0, w_store = 0;
+      long long w_tfull = 0, w_store = 0, w_ldtm = 0, w_alu = 0, w_sts = 0, w_fence = 0;
       const long long t_begin = clock64();
       for (TileIter it(tiles_m, tiles_n, false); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
@@ -440,6 +440,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int c = half * kChunksPerHalf + cc;
           const int col0 = n0 + c * kChunkCols;
           uint32_t pk[32];
+          long long tq = clock64();
           if constexpr (EPI == kEpiStore16) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -447,27 +448,36 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (!(p.dbg & 32)) {
                 tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 64 + hh * 32, v);
                 tmem_ld_wait();
+                { const long long tn = clock64(); w_ldtm += tn - tq; tq = tn; }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = j + lane;
               }
+              float f[32];
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int bl = (cc * 64 + hh * 32 + j) >> 2;   // lane holding these 4 columns' bias
                 float4 b4;
                 b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
                 b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
-                float f0 = __uint_as_float(v[j]) + b4.x, f1 = __uint_as_float(v[j + 1]) + b4.y;
-                float f2 = __uint_as_float(v[j + 2]) + b4.z, f3 = __uint_as_float(v[j + 3]) + b4.w;
-                if (p.act == kActGelu) {
-                  f0 = gelu_erf(f0); f1 = gelu_erf(f1); f2 = gelu_erf(f2); f3 = gelu_erf(f3);
-                } else if (p.act == kActRelu) {
-                  f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
-                }
-                __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
-                pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h0);
-                pk[hh * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+                f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
               }
+              // warp-uniform branch OUTSIDE the element loop (otherwise the compiler if-converts it and every element
+              // pays for GELU and ReLU even when no activation is requested)
+              if (p.act == kActGelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              } else if (p.act == kActRelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                __half2 h2 = __floats2half2_rn(f[j], f[j + 1]);
+                pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              { const long long tn = clock64(); w_alu += tn - tq; tq = tn; }
             }
           } else {
             uint32_t v[32];
@@ -497,7 +507,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                            "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                            : "memory");
             }
+            { const long long tn = clock64(); w_sts += tn - tw0 - 0; }
+            const long long tf0 = clock64();
             if (!(p.dbg & 64)) fence_proxy_async_smem();
+            w_fence += clock64() - tf0;
           } else if (pk[0] == 0x12345678u && pk[31] == 0x9abcdef0u) {
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(srow), "r"(pk[7]) : "memory");
           }
@@ -514,9 +527,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
       if (p.dbg_counters && warp == 0 && lane == 0) {
-        p.dbg_counters[blockIdx.x * 8 + 5] = w_tfull;
-        p.dbg_counters[blockIdx.x * 8 + 6] = clock64() - t_begin;
-        p.dbg_counters[blockIdx.x * 8 + 7] = w_store;
+        p.dbg_counters[blockIdx.x * 16 + 5] = w_tfull;
+        p.dbg_counters[blockIdx.x * 16 + 6] = clock64() - t_begin;
+        p.dbg_counters[blockIdx.x * 16 + 7] = w_store;
+        p.dbg_counters[blockIdx.x * 16 + 8] = w_ldtm;
+        p.dbg_counters[blockIdx.x * 16 + 9] = w_alu;
+        p.dbg_counters[blockIdx.x * 16 + 10] = w_sts;
+        p.dbg_counters[blockIdx.x * 16 + 11] = w_fence;
       }
       if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before the CTA exits
     }

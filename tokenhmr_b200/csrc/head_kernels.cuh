@@ -6,64 +6,68 @@
 namespace thmr {
 
 // CrossAttention core for a single query token (pose_transformer.py:111-124):
-//   dots = (q . k_j) * dim_head^-0.5 over the 192 context tokens, softmax, out = sum_j p_j v_j.
+//   dots = (q . k_j) * dim_head^-0.5 over the T context tokens, softmax, out = sum_j p_j v_j.
 // q (B, H*64) fp32; K/V fp16 rows of the batched to_kv GEMM output: kv[(b*T + j) * ld + koff + h*64 + d],
-// V at +voff.  One block per image, one warp per head (dim_head = 64 fixed).  out (B, H*64) fp16.
+// V at +voff.  One block per (image, head) so that B*H blocks cover the chip; thread j scores key j
+// (one 128-byte row read per thread), then 64 threads accumulate the 64 output dims over all keys
+// (coalesced 128-byte reads per key).  dim_head = 64 fixed.  out (B, H*64) fp16.
 template <int T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(T)
 dec_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ kv, int ld, int koff, int voff,
                       float scale, __half* __restrict__ out, int heads) {
-  __shared__ float sq[8][64];
-  __shared__ float sp[8][T];
-  const int b = blockIdx.x;
-  const int h = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (h >= heads) return;
+  __shared__ float sq[64];
+  __shared__ float sp[T];
+  __shared__ float red[T / 32];
+  __shared__ float so[T / 64][64];
+  const int b = blockIdx.x / heads;
+  const int h = blockIdx.x % heads;
+  const int j = threadIdx.x;
+  const int lane = j & 31, w = j >> 5;
   const int inner = heads * 64;
-  sq[h][lane] = q[static_cast<size_t>(b) * inner + h * 64 + lane];
-  sq[h][lane + 32] = q[static_cast<size_t>(b) * inner + h * 64 + lane + 32];
-  __syncwarp();
-  const __half* kb = kv + static_cast<size_t>(b) * T * ld + koff + h * 64;
-  float d[T / 32];
-  float m = -INFINITY;
+  if (j < 64) sq[j] = q[static_cast<size_t>(b) * inner + h * 64 + j];
+  __syncthreads();
+  const __half* kr = kv + (static_cast<size_t>(b) * T + j) * ld + koff + h * 64;
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < T / 32; ++i) {
-    const __half* kr = kb + static_cast<size_t>(i * 32 + lane) * ld;
-    float s = 0.f;
+  for (int c = 0; c < 64; c += 8) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(kr + c);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
 #pragma unroll
-    for (int c = 0; c < 64; c += 8) {
-      const uint4 pk = *reinterpret_cast<const uint4*>(kr + c);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h2[e]);
-        s += sq[h][c + 2 * e] * f.x + sq[h][c + 2 * e + 1] * f.y;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      s += sq[c + 2 * e] * f.x + sq[c + 2 * e + 1] * f.y;
     }
-    d[i] = s * scale;
-    m = fmaxf(m, d[i]);
   }
-  m = warp_max(m);
-  float sum = 0.f;
+  s *= scale;
+  float m = warp_max(s);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
 #pragma unroll
-  for (int i = 0; i < T / 32; ++i) {
-    d[i] = expf(d[i] - m);
-    sum += d[i];
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
+  for (int i = 1; i < T / 32; ++i) m = fmaxf(m, red[i]);
+  const float e = expf(s - m);
+  float sum = warp_sum(e);
+  __syncthreads();
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < T / 32; ++i) sp[h][i * 32 + lane] = d[i] * inv;
-  __syncwarp();
-  const __half* vb = kv + static_cast<size_t>(b) * T * ld + voff + h * 64 + 2 * lane;
-  float o0 = 0.f, o1 = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < T; ++j) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vb + static_cast<size_t>(j) * ld));
-    o0 += sp[h][j] * f.x;
-    o1 += sp[h][j] * f.y;
+  for (int i = 0; i < T / 32; ++i) sum += red[i];
+  sp[j] = e / sum;
+  __syncthreads();
+  // out[d] = sum_j p_j v[j][d]: T/64 key groups x 64 dims, then a final reduction over the groups
+  const int d = j & 63, g = j >> 6;
+  const __half* vb = kv + static_cast<size_t>(b) * T * ld + voff + h * 64 + d;
+  float o = 0.f;
+  for (int k = g; k < T; k += T / 64) o += sp[k] * __half2float(vb[static_cast<size_t>(k) * ld]);
+  so[g][d] = o;
+  __syncthreads();
+  if (j < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < T / 64; ++i) t += so[i][j];
+    out[static_cast<size_t>(b) * inner + h * 64 + j] = __float2half_rn(t);
   }
-  *reinterpret_cast<__half2*>(out + static_cast<size_t>(b) * inner + h * 64 + 2 * lane) = __floats2half2_rn(o0, o1);
 }
 
 // Read-out assembly (token_head.py:99-105,123-128) + rot6d_to_rotmat (geometry.py:64-84).
