@@ -52,44 +52,61 @@ struct Bump {
 };
 
 // ---- SMPL stage (shared by thmr_lbs / thmr_smpl_forward / the engine) -----------------------------------
+// The pose-blend offsets (fp32, 82.7 KB per pose) are produced by a GEMM and consumed by the skinning kernel.
+// Poses are processed in chunks of kSmplChunk so that the offsets of a chunk (42 MB) stay L2-resident between the
+// two kernels instead of making a round trip through HBM.
+constexpr int kSmplChunk = 512;
 struct SmplWs {
   float* A;        // [B,24,12]
   float* Jposed;   // [B,24,3]
   __half* pf16;    // [B,624]
-  float* offsets;  // [B,3V]
+  float* offsets;  // [min(B,kSmplChunk), off_pitch]
+  long off_pitch;  // 3V rounded up to 4 floats (TMA store needs 16-byte row pitch)
 };
 inline void smpl_carve(Bump& bp, const SmplModel& m, int B, SmplWs* ws) {
   ws->A = bp.take<float>(static_cast<size_t>(B) * kSmplJ * 12);
   ws->Jposed = bp.take<float>(static_cast<size_t>(B) * kSmplJ * 3);
   ws->pf16 = bp.take<__half>(static_cast<size_t>(B) * 3 * kSmplPFPad);
-  ws->offsets = bp.take<float>(static_cast<size_t>(B) * 3 * m.V);
+  ws->off_pitch = (3L * m.V + 3) / 4 * 4;
+  ws->offsets = bp.take<float>(static_cast<size_t>(B < kSmplChunk ? B : kSmplChunk) * ws->off_pitch);
+}
+
+inline int smpl_blend_plan(const SmplModel& m, const SmplWs& ws, int p0, int n, GemmPlan* plan) {
+  GemmDesc d;
+  d.A = ws.pf16 + static_cast<size_t>(p0) * 3 * kSmplPFPad; d.lda = 3 * kSmplPFPad; d.a_rows = n;
+  d.B = m.posedirsT; d.ldb = 3 * kSmplPFPad;
+  d.M = n; d.N = static_cast<int>(ws.off_pitch); d.K = 3 * kSmplPFPad;
+  d.out32 = ws.offsets; d.ld32 = static_cast<int>(ws.off_pitch);
+  d.alpha = 1.0f / (kSplitScale * kSplitScale);
+  d.force_2cta = 0;
+  return gemm_make_plan(d, plan);
 }
 
 // verts: fp32 [B,V,3];  lbs_joints (nullable): [B,24,3];  joints44 (nullable): [B,25+n_extra,3]
+// blend_plans (nullable): pre-built plans, one per chunk (engine); otherwise built on the fly.
 inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const float* betas, int B, float* verts,
                     float* lbs_joints, float* joints44, const float* pred_cam, float focal, float image_size,
-                    float* cam_t, float* focal_out, float* kp2d, const SmplWs& ws, const GemmPlan* blend_plan,
+                    float* cam_t, float* focal_out, float* kp2d, const SmplWs& ws, const GemmPlan* blend_plans,
                     cudaStream_t st) {
   const SmplModel& m = sm->m;
   smpl_pose_kernel<<<B, 32, 0, st>>>(pose, pose2rot, betas, m.J_template, m.J_shapedirs, m.nb, sm->parents_dev, ws.A,
                                      lbs_joints ? lbs_joints : ws.Jposed, ws.pf16, B);
   THMR_CUDA(cudaGetLastError());
-  GemmPlan local;
-  if (!blend_plan) {
-    GemmDesc d;
-    d.A = ws.pf16; d.lda = 3 * kSmplPFPad; d.a_rows = B;
-    d.B = m.posedirsT; d.ldb = 3 * kSmplPFPad;
-    d.M = B; d.N = 3 * m.V; d.K = 3 * kSmplPFPad;
-    d.out32 = ws.offsets; d.ld32 = 3 * m.V;
-    d.alpha = 1.0f / (kSplitScale * kSplitScale);
-    THMR_TRY(gemm_make_plan(d, &local));
-    blend_plan = &local;
+  int ci = 0;
+  for (int p0 = 0; p0 < B; p0 += kSmplChunk, ++ci) {
+    const int n = (B - p0) < kSmplChunk ? (B - p0) : kSmplChunk;
+    GemmPlan local;
+    const GemmPlan* plan = blend_plans ? &blend_plans[ci] : &local;
+    if (!blend_plans) THMR_TRY(smpl_blend_plan(m, ws, p0, n, &local));
+    THMR_TRY(gemm_launch(*plan, st));
+    dim3 grid((m.V + kSkinThreads - 1) / kSkinThreads, (n + kSkinPoses - 1) / kSkinPoses);
+    smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.v_template, m.shapedirs, m.nb, m.w_idx, m.w_val, m.ell,
+                                                    betas + static_cast<size_t>(p0) * m.nb,
+                                                    ws.A + static_cast<size_t>(p0) * kSmplJ * 12, ws.offsets, ws.off_pitch,
+                                                    verts + static_cast<size_t>(p0) * m.V * 3, static_cast<long>(m.V) * 3,
+                                                    m.V, n);
+    THMR_CUDA(cudaGetLastError());
   }
-  THMR_TRY(gemm_launch(*blend_plan, st));
-  dim3 grid((m.V + kSkinThreads - 1) / kSkinThreads, (B + kSkinPoses - 1) / kSkinPoses);
-  smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.v_template, m.shapedirs, m.nb, m.w_idx, m.w_val, m.ell, betas, ws.A,
-                                                  ws.offsets, verts, static_cast<long>(m.V) * 3, m.V, B);
-  THMR_CUDA(cudaGetLastError());
   if (joints44) {
     smpl_joints_kernel<<<B, 64, 0, st>>>(lbs_joints ? lbs_joints : ws.Jposed, verts, static_cast<long>(m.V) * 3,
                                          m.joint_map, m.extra_vid, m.jx_ptr, m.jx_idx, m.jx_val, m.n_extra, joints44,
@@ -405,15 +422,9 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     const float* ip = w.init_pose; const float* ib = w.init_betas; const float* ic = w.init_cam;
     const int nb = e->smpl->m.nb;
     const thmr_smpl* sm = e->smpl;
-    GemmPlan blend;
-    {
-      GemmDesc d;
-      d.A = sws.pf16; d.lda = 3 * kSmplPFPad; d.a_rows = B;
-      d.B = sm->m.posedirsT; d.ldb = 3 * kSmplPFPad;
-      d.M = B; d.N = 3 * sm->m.V; d.K = 3 * kSmplPFPad;
-      d.out32 = sws.offsets; d.ld32 = 3 * sm->m.V;
-      d.alpha = 1.0f / (kSplitScale * kSplitScale);
-      const int s = gemm_make_plan(d, &blend);
+    std::vector<GemmPlan> blend((B + kSmplChunk - 1) / kSmplChunk);
+    for (int ci = 0, p0 = 0; p0 < B; p0 += kSmplChunk, ++ci) {
+      const int s = smpl_blend_plan(sm->m, sws, p0, (B - p0) < kSmplChunk ? (B - p0) : kSmplChunk, &blend[ci]);
       if (s != THMR_OK) err = s;
     }
     const float focal = c.focal_length, isz = static_cast<float>(c.image_size);
@@ -429,7 +440,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
       float* kp2 = r.out.pred_keypoints_2d ? r.out.pred_keypoints_2d : kp2_fb;
       float* camt = r.out.pred_cam_t ? r.out.pred_cam_t : camt_fb;
       float* foc = r.out.focal_length ? r.out.focal_length : focal_fb;
-      return smpl_run(sm, rot, 0, bet, B, verts, nullptr, kp3, cam, focal, isz, camt, foc, kp2, sws, &blend, st);
+      return smpl_run(sm, rot, 0, bet, B, verts, nullptr, kp3, cam, focal, isz, camt, foc, kp2, sws, blend.data(), st);
     });
   }
   *status = err;

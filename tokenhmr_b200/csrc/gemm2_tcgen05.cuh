@@ -31,7 +31,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int ksplit) {
-  static_assert(EPI == kEpiStore16 || EPI == kEpiAdd32, "2-CTA GEMM supports the TMA epilogues only");
+  static_assert(EPI == kEpiStore16 || EPI == kEpiAdd32 || EPI == kEpiStore32, "2-CTA GEMM supports the TMA epilogues only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kG2BarOffset);   // used in the leader only
@@ -233,10 +233,10 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             float4 b4;
             b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
             b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
-            pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
-            pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
-            pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
-            pk[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b4.w);
+            pk[j] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j]), b4.x));
+            pk[j + 1] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 1]), b4.y));
+            pk[j + 2] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 2]), b4.z));
+            pk[j + 3] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 3]), b4.w));
           }
         }
         if (lane == 0) tma_store_wait_read<0>();
@@ -251,6 +251,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         __syncwarp();
         if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
           if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+          else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
           else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
           tma_store_commit();
         }

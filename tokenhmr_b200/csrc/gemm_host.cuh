@@ -39,12 +39,14 @@ struct GemmDesc {
 
 // Which epilogue can serve this GEMM (see gemm_tcgen05.cuh).
 inline int pick_epi(const GemmDesc& d) {
-  const bool plain = !d.argmin_out && d.seq_pitch == 0 && d.alpha == 1.0f && d.resid_mod == 0 && !d.act32 &&
-                     d.N % 8 == 0 && d.M >= kGemmBM && (!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
+  const bool plain = !d.argmin_out && d.seq_pitch == 0 && d.resid_mod == 0 && !d.act32 && d.N % 4 == 0 &&
+                     d.M >= kGemmBM && (!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
   if (!plain) return kEpiGeneric;
-  if (d.out16 && !d.out32 && !d.resid && d.ld16 % 8 == 0) return kEpiStore16;
-  if (d.out32 && !d.out16 && d.resid == d.out32 && d.ldr == d.ld32 && d.act == kActNone && d.ld32 % 4 == 0)
+  if (d.out16 && !d.out32 && !d.resid && d.ld16 % 8 == 0 && d.N % 8 == 0 && d.alpha == 1.0f) return kEpiStore16;
+  if (d.out32 && !d.out16 && d.resid == d.out32 && d.ldr == d.ld32 && d.act == kActNone && d.ld32 % 4 == 0 &&
+      d.alpha == 1.0f)
     return kEpiAdd32;
+  if (d.out32 && !d.out16 && !d.resid && d.act == kActNone && d.ld32 % 4 == 0) return kEpiStore32;
   return kEpiGeneric;
 }
 
@@ -113,7 +115,7 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   if (epi == kEpiStore16)
     THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, 32, 64,
                           CU_TENSOR_MAP_SWIZZLE_128B));
-  else if (epi == kEpiAdd32)
+  else if (epi == kEpiAdd32 || epi == kEpiStore32)
     THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out32, d.M, d.N, d.ld32, 32, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B));
   else
@@ -177,6 +179,7 @@ inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (plan.two_cta) {
     if (plan.epi == kEpiStore16) return gemm2_launch_t<kEpiStore16>(plan, stream);
     if (plan.epi == kEpiAdd32) return gemm2_launch_t<kEpiAdd32>(plan, stream);
+    if (plan.epi == kEpiStore32) return gemm2_launch_t<kEpiStore32>(plan, stream);
     return fail(THMR_ERR_INVALID, "gemm: CTA-pair kernel needs a TMA epilogue");
   }
   if (plan.epi == kEpiStore16) {
@@ -185,6 +188,9 @@ inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   } else if (plan.epi == kEpiAdd32) {
     if (plan.bn == 256) return gemm_launch_t<256, 4, kEpiAdd32>(plan, stream);
     if (plan.bn == 128) return gemm_launch_t<128, 6, kEpiAdd32>(plan, stream);
+  } else if (plan.epi == kEpiStore32) {
+    if (plan.bn == 256) return gemm_launch_t<256, 4, kEpiStore32>(plan, stream);
+    if (plan.bn == 128) return gemm_launch_t<128, 6, kEpiStore32>(plan, stream);
   } else {
     switch (plan.bn) {
       case 256: return gemm_launch_t<256, 4, kEpiGeneric>(plan, stream);

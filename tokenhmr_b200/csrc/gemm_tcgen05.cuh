@@ -13,6 +13,7 @@
 //   kEpiGeneric : tcgen05.ld -> bias / residual / activation -> direct global stores; handles every option
 //                 (two outputs, residual tables, padded-sequence masking, row-argmin).  Used by the small-M tail.
 //   kEpiStore16 : act(acc + bias) -> fp16 -> 128B-swizzled smem -> TMA store            (QKV, fc1+GELU, to_kv)
+//   kEpiStore32 : alpha * acc + bias, fp32 -> swizzled smem -> TMA store                 (SMPL pose-blend offsets)
 //   kEpiAdd32   : (acc + bias) fp32 -> swizzled smem -> TMA reduce-add into the output   (proj / fc2: x += ...)
 //                 the residual add happens in the L2 reduction unit, the residual is never read by the SM.
 //
@@ -24,7 +25,7 @@
 namespace thmr {
 
 enum : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
-enum : int { kEpiGeneric = 0, kEpiStore16 = 1, kEpiAdd32 = 2 };
+enum : int { kEpiGeneric = 0, kEpiStore16 = 1, kEpiAdd32 = 2, kEpiStore32 = 3 };
 
 struct GemmParams {
   int M, N, K;
@@ -285,6 +286,15 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const float* rrow = nullptr;
         if (p.resid) rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? row % p.resid_mod : row) * p.ldr;
 
+        // row-argmin: this warp's column norms (lane l: 4 columns of its column half) and the row norm are
+        // fetched while the MMAs run; the inner loop then only shuffles
+        float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+        float x2 = 0.f;
+        if (p.argmin_out) {
+          const int bc = n0 + half * kChunksPerHalf * 32 + lane * 4;
+          if (lane * 4 < kChunksPerHalf * 32 && bc + 3 < p.N) cq = __ldg(reinterpret_cast<const float4*>(p.col_sq + bc));
+          if (row_ok) x2 = __ldg(p.row_sq + row);
+        }
         if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one polling lane per warp
         __syncwarp();
         tc_fence_after();
@@ -297,14 +307,18 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
           if (p.argmin_out) {
-            if (row_ok && col0 < p.N) {
-              const float x2 = __ldg(p.row_sq + row);
+            if (col0 < p.N) {   // (warp-uniform: shuffles below need every lane)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + j < p.N) {
+              for (int j = 0; j < 32; j += 4) {
+                const int bl = (cc * 32 + j) >> 2;
+                float c2[4];
+                c2[0] = __shfl_sync(0xffffffffu, cq.x, bl); c2[1] = __shfl_sync(0xffffffffu, cq.y, bl);
+                c2[2] = __shfl_sync(0xffffffffu, cq.z, bl); c2[3] = __shfl_sync(0xffffffffu, cq.w, bl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
                   // same expression order as the reference: (sum x^2 - 2 x.c) + sum c^2
-                  const float d = (x2 - 2.0f * (p.alpha * __uint_as_float(v[j]))) + __ldg(p.col_sq + col0 + j);
-                  if (d < best) { best = d; best_idx = col0 + j; }
+                  const float d = (x2 - 2.0f * (p.alpha * __uint_as_float(v[j + e]))) + c2[e];
+                  if (col0 + j + e < p.N && d < best) { best = d; best_idx = col0 + j + e; }
                 }
               }
             }
@@ -489,10 +503,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float4 b4;
               b4.x = __shfl_sync(0xffffffffu, bq.x, bl); b4.y = __shfl_sync(0xffffffffu, bq.y, bl);
               b4.z = __shfl_sync(0xffffffffu, bq.z, bl); b4.w = __shfl_sync(0xffffffffu, bq.w, bl);
-              pk[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
-              pk[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
-              pk[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
-              pk[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b4.w);
+              pk[j] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j]), b4.x));
+              pk[j + 1] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 1]), b4.y));
+              pk[j + 2] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 2]), b4.z));
+              pk[j + 3] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 3]), b4.w));
             }
           }
           // the previous TMA store of this warp must have finished reading the staging tile
@@ -517,6 +531,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
             if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
             else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
             tma_store_commit();
           }

@@ -183,19 +183,22 @@ smpl_pose_kernel(const float* __restrict__ pose, int pose2rot, const float* __re
 
 // ---- skinning: thread = vertex, block = 128 vertices x SKIN_POSES poses ---------------------------------
 constexpr int kSkinPoses = 16;
+constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used): odd stride -> distinct joints hit distinct banks
 constexpr int kSkinThreads = 128;
 
 __global__ void __launch_bounds__(kSkinThreads)
 smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs, int nb,
                  const int* __restrict__ w_idx, const float* __restrict__ w_val, int ell,
                  const float* __restrict__ betas, const float* __restrict__ A, const float* __restrict__ offsets,
-                 float* __restrict__ verts, long vert_pitch /* floats between poses in `verts` */, int V, int B) {
-  __shared__ float sA[kSkinPoses][kSmplJ * 12];
+                 long off_pitch, float* __restrict__ verts, long vert_pitch /* floats between poses */, int V, int B) {
+  __shared__ float sA[kSkinPoses][kSmplJ * kSkinAStride];
   __shared__ float sB[kSkinPoses][16];
   const int p0 = blockIdx.y * kSkinPoses;
   const int np = (B - p0) < kSkinPoses ? (B - p0) : kSkinPoses;
-  for (int i = threadIdx.x; i < np * kSmplJ * 12; i += kSkinThreads)
-    sA[i / (kSmplJ * 12)][i % (kSmplJ * 12)] = A[static_cast<size_t>(p0) * kSmplJ * 12 + i];
+  for (int i = threadIdx.x; i < np * kSmplJ * 12; i += kSkinThreads) {
+    const int r = i % (kSmplJ * 12);
+    sA[i / (kSmplJ * 12)][(r / 12) * kSkinAStride + r % 12] = A[static_cast<size_t>(p0) * kSmplJ * 12 + i];
+  }
   for (int i = threadIdx.x; i < np * nb; i += kSkinThreads) sB[i / nb][i % nb] = betas[static_cast<size_t>(p0) * nb + i];
   __syncthreads();
   const int v = blockIdx.x * kSkinThreads + threadIdx.x;
@@ -207,9 +210,18 @@ smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__
 #pragma unroll
     for (int l = 0; l < 10; ++l) sd[c][l] = (l < nb) ? shapedirs[(static_cast<size_t>(v) * 3 + c) * nb + l] : 0.f;
   }
+  // skinning weights of this vertex: registers when the ELL width is small (real SMPL: 4), else re-read
+  constexpr int kEllReg = 8;
+  int wi[kEllReg];
+  float wv[kEllReg];
+#pragma unroll
+  for (int k = 0; k < kEllReg; ++k) {
+    wi[k] = (k < ell) ? w_idx[static_cast<size_t>(v) * ell + k] : 0;
+    wv[k] = (k < ell) ? w_val[static_cast<size_t>(v) * ell + k] : 0.f;
+  }
   for (int pp = 0; pp < np; ++pp) {
     const int b = p0 + pp;
-    const float* off = offsets + static_cast<size_t>(b) * V * 3 + v * 3;
+    const float* off = offsets + static_cast<size_t>(b) * off_pitch + v * 3;
     float x[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -221,11 +233,23 @@ smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__
     float T[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) T[e] = 0.f;
-    for (int k = 0; k < ell; ++k) {
-      const float w = w_val[static_cast<size_t>(v) * ell + k];
-      const float* a = &sA[pp][w_idx[static_cast<size_t>(v) * ell + k] * 12];
+    if (ell <= kEllReg) {
 #pragma unroll
-      for (int e = 0; e < 12; ++e) T[e] += w * a[e];
+      for (int k = 0; k < kEllReg; ++k) {
+        if (k < ell) {
+          const float w = wv[k];
+          const float* a = &sA[pp][wi[k] * kSkinAStride];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] += w * a[e];
+        }
+      }
+    } else {
+      for (int k = 0; k < ell; ++k) {
+        const float w = w_val[static_cast<size_t>(v) * ell + k];
+        const float* a = &sA[pp][w_idx[static_cast<size_t>(v) * ell + k] * kSkinAStride];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] += w * a[e];
+      }
     }
     float* o = verts + static_cast<size_t>(b) * vert_pitch + v * 3;
 #pragma unroll

@@ -112,7 +112,7 @@ size_t thmr_vq_workspace_bytes(int64_t Q, int K, int D) {
 int thmr_vq_argmin(const float* x, int64_t Q, const float* codebook, int K, int D, int64_t* idx, void* workspace,
                    void* stream) {
   THMR_CHECK(x && codebook && idx && workspace, "vq_argmin: null argument");
-  THMR_CHECK(D % 64 == 0 && Q > 0 && K > 0 && Q < (1ll << 31), "vq_argmin: unsupported shape Q=%lld K=%d D=%d",
+  THMR_CHECK(D % 64 == 0 && Q > 0 && K > 0 && K % 4 == 0 && Q < (1ll << 31), "vq_argmin: unsupported shape Q=%lld K=%d D=%d",
              (long long)Q, K, D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Bump bp(workspace);
@@ -195,7 +195,13 @@ int thmr_smpl_create(const thmr_smpl_desc* d, thmr_smpl** out) {
   // posedirs -> transposed split fp16
   float* pd = nullptr;
   SM_TRY(dev_clone(&pd, d->posedirs, static_cast<size_t>(kSmplPF) * 3 * V));
-  SM_TRY(dev_alloc(&m.posedirsT, static_cast<size_t>(3) * V * 3 * kSmplPFPad));
+  {
+    // rows padded to a multiple of 4 (zero rows): the blend GEMM's N equals the 16-byte aligned offsets pitch
+    const size_t rows_pad = (static_cast<size_t>(3) * V + 3) / 4 * 4;
+    SM_TRY(dev_alloc(&m.posedirsT, rows_pad * 3 * kSmplPFPad));
+    if (cudaMemset(m.posedirsT, 0, rows_pad * 3 * kSmplPFPad * sizeof(__half)) != cudaSuccess)
+      return bail(fail(THMR_ERR_CUDA, "smpl_create: memset posedirs"));
+  }
   {
     const long n = static_cast<long>(3) * V * kSmplPFPad;
     smpl_pack_posedirs_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(pd, m.posedirsT, 3 * V);
