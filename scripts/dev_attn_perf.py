@@ -16,4 +16,5 @@ run(3, False)
 print(f"attention bs=64: L2-warm {run(20, False)*1e3:.1f} us, L2-flushed {run(20, True)*1e3:.1f} us per layer")
 c = cnt.view(148, 16).float().mean(0).tolist()
 print(f"MMA thread: wait qk_full {c[0]:.0f} o_empty {c[1]:.0f} v_full {c[2]:.0f} p_full {c[3]:.0f} / total {c[4]:.0f}")
+print(f"softmax detail: ldtm {c[5]:.0f} max+xchg {c[6]:.0f} exp {c[7]:.0f} (p_empty wait+STS+fence, from p_empty wait start) {c[13]:.0f} epi(o_full wait+ld+store) {c[14]:.0f}")
 print(f"softmax warp(q=0,h=0): wait s_full {c[8]:.0f} p_empty {c[9]:.0f} o_full {c[10]:.0f} pairbar {c[11]:.0f} / total {c[12]:.0f}  (7 heads per CTA)")

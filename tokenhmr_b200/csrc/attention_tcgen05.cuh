@@ -40,6 +40,7 @@ struct AttnParams {
   int ldo;
   float* dbg_s;      // optional [B*H, 192, 192] raw scores (tests only)
   unsigned long long* dbg_counters;  // optional [gridDim.x][16] cycle counters (THMR_ATTN_COUNTERS)
+  int p_in_tmem;     // experiment (THMR_ATTN_TS=1): P also written to TMEM cols [384,480) and PV issued in TS mode
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -158,7 +159,8 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
           for (int ks = 0; ks < kAttTokens / 16; ++ks) {
             const uint64_t da = make_smem_desc(sPa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kSwz128);
             const uint64_t db = make_smem_desc(sVa + ks * 512, kAttChunkBytes, 256, kSwz32);
-            umma_f16_ss(tmem_base + t * kAttTokens, da, db, idesc_o, ks != 0);
+            if (p.p_in_tmem) umma_f16_ts(tmem_base + t * kAttTokens, tmem_base + 384 + ks * 8, db, idesc_o, ks != 0);
+            else umma_f16_ss(tmem_base + t * kAttTokens, da, db, idesc_o, ks != 0);
           }
           umma_commit(&o_full[t]);
           umma_commit(p_empty);
@@ -177,7 +179,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
     const int trow = q * 32 + lane;      // row inside the 128-row tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     int i = 0;
-    long long w_s = 0, w_pe = 0, w_of = 0, w_bar = 0;
+    long long w_s = 0, w_pe = 0, w_of = 0, w_bar = 0, w_ld = 0, w_max = 0, w_exp = 0, w_sts = 0, w_epi = 0;
     const long long t_begin = clock64();
     for (int prob = blockIdx.x; prob < p.num_problems; prob += gridDim.x, ++i) {
       const int b = prob / p.heads, h = prob % p.heads;
@@ -191,6 +193,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
         float sum = 0.f;
         if (active) {
           float s[96];
+          long long tph = clock64();
           {
             uint32_t v[32];
 #pragma unroll
@@ -206,6 +209,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
 #pragma unroll
             for (int e = 0; e < 96; ++e) d[e] = s[e];
           }
+          { const long long tn = clock64(); w_ld += tn - tph; tph = tn; }
           float m = s[0];
 #pragma unroll
           for (int e = 1; e < 96; ++e) m = fmaxf(m, s[e]);
@@ -214,6 +218,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
           named_bar_sync(1 + q, 64);
           w_bar += clock64() - t0;
           m = fmaxf(m, smax[(t * 2 + (half ^ 1)) * 128 + trow]);
+          { const long long tn = clock64(); w_max += tn - tph; tph = tn; }
           const float mo = m * p.scale_log2e;
 #pragma unroll
           for (int e = 0; e < 96; e += 2) {
@@ -224,6 +229,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h2);
           }
           ssum[(t * 2 + half) * 128 + trow] = sum;
+          { const long long tn = clock64(); w_exp += tn - tph; tph = tn; }
         }
         t0 = clock64();
         mbar_wait(p_empty, t ^ 1);       // PV of the previous tile has finished reading P
@@ -239,10 +245,22 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
                          : "memory");
           }
         }
+        if (p.p_in_tmem) {
+          // all 32 lanes participate (.sync.aligned); rows of inactive warps carry stale registers (results unused)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            uint32_t w16[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) w16[e] = pk[c * 16 + e];
+            tmem_st_x16(tmem_base + lane_addr + 384 + half * 48 + c * 16, w16);
+          }
+          tmem_st_wait();
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (active) w_sts += clock64() - t0 ;
       }
       for (int t = 0; t < 2; ++t) {
         const bool active = (t == 0) || (q >= 2);
@@ -273,6 +291,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
             *reinterpret_cast<uint4*>(o + j * 16 + 8) = w1;
           }
         }
+        if (active) w_epi += clock64() - t0;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_empty[t]);
@@ -281,6 +300,7 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams
     if (p.dbg_counters && warp == 4 && lane == 0) {
       unsigned long long* c = p.dbg_counters + blockIdx.x * 16;
       c[8] = w_s; c[9] = w_pe; c[10] = w_of; c[11] = w_bar; c[12] = clock64() - t_begin;
+      c[5] = w_ld; c[6] = w_max; c[7] = w_exp; c[13] = w_sts; c[14] = w_epi;
     }
   }
 
@@ -326,6 +346,7 @@ inline int attention_make_plan(const __half* qkv, int ld_qkv, int B, int heads, 
   plan->p.out = out;
   plan->p.ldo = ldo;
   plan->p.dbg_s = dbg_s;
+  { const char* e = getenv("THMR_ATTN_TS"); plan->p.p_in_tmem = e ? atoi(e) : 0; }
   { const char* e = getenv("THMR_ATTN_COUNTERS"); plan->p.dbg_counters = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   plan->grid = plan->p.num_problems < num_sms() ? plan->p.num_problems : num_sms();
   return THMR_OK;

@@ -6,7 +6,7 @@
 #include <functional>
 #include <vector>
 
-#include "attention_tcgen05.cuh"
+#include "attention2_tcgen05.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_host.cuh"
@@ -270,7 +270,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
       AttnPlan ap;
       const int s = attention_make_plan(qkv, 3 * D, B, H, ao, D, nullptr, &ap);
       if (s != THMR_OK) err = s;
-      S.push_back([ap](const RunCtx&, cudaStream_t st) -> int { return attention_launch(ap, st); });
+      S.push_back([ap](const RunCtx&, cudaStream_t st) -> int { return attention_dispatch(ap, st); });
     }
     S.tag("vit.proj_gemm");
     linear(ao, D, M, bw.proj_w, D, D, bw.proj_b, kActNone, x, nullptr, x);

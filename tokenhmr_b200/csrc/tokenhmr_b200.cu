@@ -96,7 +96,7 @@ int thmr_vit_attention(const void* qkv, int B, int heads, void* out, float* dbg_
   AttnPlan plan;
   THMR_TRY(attention_make_plan(static_cast<const __half*>(qkv), 3 * heads * kAttHeadDim, B, heads,
                                static_cast<__half*>(out), heads * kAttHeadDim, dbg_scores, &plan));
-  return attention_launch(plan, static_cast<cudaStream_t>(stream));
+  return attention_dispatch(plan, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ VQ
