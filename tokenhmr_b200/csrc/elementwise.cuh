@@ -1,6 +1,8 @@
 // HBM-bound row kernels: patch im2col, LayerNorm, softmax, gathers.  Warp-shuffle reductions, fp32 math,
 // vectorised coalesced loads; outputs are written in the operand format of the consuming tcgen05 GEMM (fp16).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace thmr {
@@ -57,9 +59,11 @@ __global__ void __launch_bounds__(256)
 layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu,
                      int out_t) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= R) return;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  // persistent warps: the grid is sized to the resident capacity and every warp walks rows with a grid stride,
+  // so no time is lost re-scheduling blocks between rows
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < R; warp += warps_total) {
   const float* xr = x + static_cast<size_t>(warp) * C;
   float4 v[VEC4];
   float s = 0.f;
@@ -110,6 +114,7 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       }
     }
   }
+  }   // row loop
 }
 
 // Wide rows (C up to 64K, e.g. the 10240-wide FCBlock norm): one block per row, three passes over L1/L2.
@@ -154,7 +159,10 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
   if (ld16 == 0) ld16 = C;
   if (C <= 2048) {
     const int threads = 256, rows_per_block = threads / 32;
-    const int grid = (R + rows_per_block - 1) / rows_per_block;
+    int grid = (R + rows_per_block - 1) / rows_per_block;
+    const int resident = num_sms() * 4;   // 4 blocks of 256 threads per SM at 64 registers
+    static const int persist = [] { const char* e = getenv("THMR_LN_PERSIST"); return e ? atoi(e) : 1; }();
+    if (persist && grid > resident * persist) grid = resident * persist;
     const int vec4 = (C / 4 + 31) / 32;
     if (vec4 <= 1) layernorm_reg_kernel<1><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
     else if (vec4 <= 8) layernorm_reg_kernel<8><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
