@@ -1,7 +1,7 @@
 #!/bin/bash
 # same-box A/B of engine variants: prints ms/step and the family table for each env setting
 export PYTHONPATH=.
-for cfg in "base" "THMR_ATTN_V2=0" "THMR_ATTN_SLOTS=2" "THMR_GEMM_2CTA=0" "THMR_GEMM_SPLITK=1"; do
+for cfg in ${AB_CFGS:-base THMR_ATTN_GEN=2 THMR_ATTN_GEN=1 THMR_GEMM_2CTA=0}; do
   if [ "$cfg" = "base" ]; then envs=""; else envs="$cfg"; fi
   env $envs timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys

@@ -277,10 +277,4 @@ inline int attention2_launch(const AttnPlan& plan, cudaStream_t st) {
   return slots == 2 ? attention2_launch_t<2>(plan, st) : attention2_launch_t<1>(plan, st);
 }
 
-// THMR_ATTN_V2=0 selects the first-generation kernel (one CTA per SM, P through shared memory).
-inline int attention_dispatch(const AttnPlan& plan, cudaStream_t st) {
-  static const int v2 = [] { const char* e = getenv("THMR_ATTN_V2"); return e ? atoi(e) : 1; }();
-  return v2 ? attention2_launch(plan, st) : attention_launch(plan, st);
-}
-
 }  // namespace thmr

@@ -330,6 +330,7 @@ inline int make_tmap_qkv(CUtensorMap* out, const void* qkv, uint64_t rows, uint6
 
 struct AttnPlan {
   CUtensorMap tm;
+  CUtensorMap tm_out;   // [B*192, H*80] fp16 output, 32-row x 80-column boxes (third-generation kernel)
   AttnParams p;
   int grid;
 };
@@ -340,6 +341,8 @@ inline int attention_make_plan(const __half* qkv, int ld_qkv, int B, int heads, 
   THMR_CHECK(ld_qkv >= 3 * heads * kAttHeadDim, "attention: qkv pitch %d < %d", ld_qkv, 3 * heads * kAttHeadDim);
   THMR_CHECK(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: output alignment");
   THMR_TRY(make_tmap_qkv(&plan->tm, qkv, static_cast<uint64_t>(B) * kAttTokens, ld_qkv));
+  THMR_TRY(make_tmap_2d_f16(&plan->tm_out, out, static_cast<uint64_t>(B) * kAttTokens,
+                            static_cast<uint64_t>(heads) * kAttHeadDim, ldo, 32, kAttHeadDim, CU_TENSOR_MAP_SWIZZLE_NONE));
   plan->p.num_problems = B * heads;
   plan->p.heads = heads;
   plan->p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kAttHeadDim));

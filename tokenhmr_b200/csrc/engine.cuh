@@ -6,7 +6,7 @@
 #include <functional>
 #include <vector>
 
-#include "attention2_tcgen05.cuh"
+#include "attention3_tcgen05.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_host.cuh"

@@ -69,8 +69,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (no hardware suspend window, unlike try_wait): for pollers that multiplex several barriers.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait; returns false (and raises the global flag) on timeout.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1   // the compiler otherwise unrolls every spin loop x4: pure instruction-cache pressure
   for (uint32_t it = 0; it < kSpinLimit; ++it) {
     if (mbar_try_wait(bar, parity)) return true;
   }
@@ -192,6 +207,14 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Orders later uses of v[] after a preceding tcgen05.wait::ld when loads are software-pipelined (the compiler
+// sees no data dependence between the wait and the registers an earlier tcgen05.ld filled).
+template <int N>
+__device__ __forceinline__ void tmem_pin(uint32_t (&v)[N]) {
+#pragma unroll
+  for (int e = 0; e < N; ++e) asm volatile("" : "+r"(v[e]));
+}
 
 // registers -> TMEM (32x32b, 16 columns): thread t writes lane (base_lane + t).
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
