@@ -54,67 +54,91 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __half* __res
 //       y16[(r / T) * C * T + c * T + (r % T)]   (MixerLayer token mixing, modules.py:56-59)
 //   Row pitch of the fp16 output is ld16 (elements) when not transposed.
 // ------------------------------------------------------------------------------------------------
-template <int VEC4>  // float4 loads per lane
-__global__ void __launch_bounds__(256)
+template <int VEC4, bool PREFETCH>  // float4 loads per lane; PREFETCH: the next row's loads are issued before this row's math
+__global__ void __launch_bounds__(256, VEC4 > 10 ? (PREFETCH ? 1 : 2) : (PREFETCH ? 2 : 4))
 layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu,
                      int out_t) {
+  // gamma/beta staged in shared memory once per (persistent) block: read from global inside the output loop they
+  // were the largest stall of the kernel (an L2-latency load per 4 outputs, after the reductions)
+  extern __shared__ float4 s_gb[];   // [2][C/4]
+  float4* sg = s_gb;
+  float4* sb = s_gb + C / 4;
+  for (int c = threadIdx.x; c < C / 4; c += blockDim.x) {
+    sg[c] = reinterpret_cast<const float4*>(gamma)[c];
+    sb[c] = reinterpret_cast<const float4*>(beta)[c];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  // persistent warps: the grid is sized to the resident capacity and every warp walks rows with a grid stride,
-  // so no time is lost re-scheduling blocks between rows
-  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < R; warp += warps_total) {
-  const float* xr = x + static_cast<size_t>(warp) * C;
-  float4 v[VEC4];
-  float s = 0.f;
+  auto load_row = [&](float4 (&v)[VEC4], int row) {
+    const float* xr = x + static_cast<size_t>(row) * C;
 #pragma unroll
-  for (int i = 0; i < VEC4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    v[i] = (c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-  }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < C) {
-      const float a = v[i].x - mean, b = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
-      q += a * a + b * b + d * d + e * e;
+    for (int i = 0; i < VEC4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      v[i] = (c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  };
+  // persistent warps: the grid is sized to the resident capacity and every warp walks rows with a grid stride
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float4 v[VEC4];
+  if (PREFETCH && warp < R) load_row(v, warp);
+  for (; warp < R; warp += warps_total) {
+    float4 nx[VEC4];
+    if (PREFETCH) {
+      if (warp + warps_total < R) load_row(nx, warp + warps_total);
+    } else {
+      load_row(v, warp);
+    }
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < C) {
-      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-      const float4 bb = *reinterpret_cast<const float4*>(beta + c);
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + bb.x;
-      o.y = (v[i].y - mean) * rstd * g.y + bb.y;
-      o.z = (v[i].z - mean) * rstd * g.z + bb.z;
-      o.w = (v[i].w - mean) * rstd * g.w + bb.w;
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      if (y32) *reinterpret_cast<float4*>(y32 + static_cast<size_t>(warp) * C + c) = o;
-      if (y16) {
-        if (out_t > 0) {
-          __half* base = y16 + static_cast<size_t>(warp / out_t) * C * out_t + (warp % out_t);
-          base[static_cast<size_t>(c) * out_t] = __float2half_rn(o.x);
-          base[static_cast<size_t>(c + 1) * out_t] = __float2half_rn(o.y);
-          base[static_cast<size_t>(c + 2) * out_t] = __float2half_rn(o.z);
-          base[static_cast<size_t>(c + 3) * out_t] = __float2half_rn(o.w);
-        } else {
-          __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(y16 + static_cast<size_t>(warp) * ld16 + c) = pk;
+    for (int i = 0; i < VEC4; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        const float a = v[i].x - mean, b = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+        q += a * a + b * b + d * d + e * e;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int i = 0; i < VEC4; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        const float4 g = sg[c >> 2];
+        const float4 bb = sb[c >> 2];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+        o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+        o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+        o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (y32) *reinterpret_cast<float4*>(y32 + static_cast<size_t>(warp) * C + c) = o;
+        if (y16) {
+          if (out_t > 0) {
+            __half* base = y16 + static_cast<size_t>(warp / out_t) * C * out_t + (warp % out_t);
+            base[static_cast<size_t>(c) * out_t] = __float2half_rn(o.x);
+            base[static_cast<size_t>(c + 1) * out_t] = __float2half_rn(o.y);
+            base[static_cast<size_t>(c + 2) * out_t] = __float2half_rn(o.z);
+            base[static_cast<size_t>(c + 3) * out_t] = __float2half_rn(o.w);
+          } else {
+            __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(y16 + static_cast<size_t>(warp) * ld16 + c) = pk;
+          }
         }
       }
     }
+    if (PREFETCH) {
+#pragma unroll
+      for (int i = 0; i < VEC4; ++i) v[i] = nx[i];
+    }
   }
-  }   // row loop
 }
 
 // Wide rows (C up to 64K, e.g. the 10240-wide FCBlock norm): one block per row, three passes over L1/L2.
@@ -160,14 +184,24 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
   if (C <= 2048) {
     const int threads = 256, rows_per_block = threads / 32;
     int grid = (R + rows_per_block - 1) / rows_per_block;
-    const int resident = num_sms() * 4;   // 4 blocks of 256 threads per SM at 64 registers
-    static const int persist = [] { const char* e = getenv("THMR_LN_PERSIST"); return e ? atoi(e) : 1; }();
-    if (persist && grid > resident * persist) grid = resident * persist;
+    static const int prefetch = [] { const char* e = getenv("THMR_LN_PREFETCH"); return e ? atoi(e) : 0; }();
+    const int resident = num_sms() * (prefetch ? 2 : 4);   // blocks of 256 threads per SM (64 / ~110 registers)
+    if (grid > resident) grid = resident;
+    THMR_CHECK(C % 4 == 0, "layernorm: C must be a multiple of 4");
+    const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
     const int vec4 = (C / 4 + 31) / 32;
-    if (vec4 <= 1) layernorm_reg_kernel<1><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
-    else if (vec4 <= 8) layernorm_reg_kernel<8><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
-    else if (vec4 <= 10) layernorm_reg_kernel<10><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
-    else layernorm_reg_kernel<16><<<grid, threads, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t);
+#define THMR_LN_LAUNCH(V)                                                                                           \
+  do {                                                                                                             \
+    if (prefetch) layernorm_reg_kernel<V, true><<<grid, threads, smem, st>>>(x, gamma, beta, y16, ld16, y32, R, C, \
+                                                                            eps, relu, out_t);                    \
+    else layernorm_reg_kernel<V, false><<<grid, threads, smem, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps,    \
+                                                                     relu, out_t);                                \
+  } while (0)
+    if (vec4 <= 1) THMR_LN_LAUNCH(1);
+    else if (vec4 <= 8) THMR_LN_LAUNCH(8);
+    else if (vec4 <= 10) THMR_LN_LAUNCH(10);
+    else THMR_LN_LAUNCH(16);
+#undef THMR_LN_LAUNCH
   } else {
     THMR_CHECK(out_t == 0, "layernorm: transposed output needs C <= 2048");
     layernorm_wide_kernel<<<R, 256, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu);
