@@ -92,6 +92,26 @@ int thmr_vq_dequant_logits(const void* logits16, int64_t Q, int K, const void* c
 int thmr_rot6d_to_rotmat(const float* x6, int64_t N, float* rot, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Evaluation metrics and the crop->full camera (the consumers of the forward's outputs)
+ * ---------------------------------------------------------------------------------------------- */
+/* torch.matmul(J_regressor_24_SMPL, vertices) [tokenhmr/lib/utils/pose_utils.py:213,219]:
+ *   jreg fp32 [J,V] (dense), verts fp32 [B,V,3] -> joints fp32 [B,J,3]. */
+int thmr_regress_joints(const float* jreg, int J, const float* verts, int V, int B, float* joints, void* stream);
+/* Evaluator.__call__ + eval_pose + reconstruction_error + compute_similarity_transform
+ * [tokenhmr/lib/utils/pose_utils.py:61-143,201-275], one batch, results in millimetres:
+ *   pred_kp fp32 [B,J,3]; gt_kp fp32 [B,J,gt_stride] (gt_stride 3, or 4 when the confidence column is still there);
+ *   keypoint_list int32 [K] device (K <= 64); pelvis = (kp[pelvis_a] + kp[pelvis_b]) / 2 of each set
+ *   (pelvis_a == pelvis_b: 3DPW branch; 1,2: EMDB branch); pred_verts / gt_verts fp32 [B,V,3] (both NULL with pve
+ *   NULL to skip the per-vertex error); mpjpe, re (PA-MPJPE), pve fp32 [B]. */
+int thmr_eval_pose(const float* pred_kp, const float* gt_kp, int gt_stride, int J, const int32_t* keypoint_list, int K,
+                   int pelvis_a, int pelvis_b, const float* pred_verts, const float* gt_verts, int V, int B,
+                   float* mpjpe, float* re, float* pve, void* stream);
+/* cam_crop_to_full [tokenhmr/lib/utils/renderer.py:13-23]: cam fp32 [B,3] (s,tx,ty), box_center [B,2], box_size [B],
+ *   img_size [B,2] (w,h) -> full_cam fp32 [B,3] (tx,ty,tz). */
+int thmr_cam_crop_to_full(const float* cam, const float* box_center, const float* box_size, const float* img_size,
+                          float focal_length, int B, float* full_cam, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SMPL body model (smplx==0.1.28 SMPLLayer / lbs, wrapped by tokenhmr/lib/models/smpl_wrapper.py:10-41)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thmr_smpl thmr_smpl;

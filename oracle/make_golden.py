@@ -92,14 +92,55 @@ def stage_goldens(ns) -> None:
     print("wrote stage goldens")
 
 
+def eval_goldens() -> None:
+    """Evaluator / eval_pose / compute_similarity_transform (pose_utils.py:61-275) and cam_crop_to_full
+    (renderer.py:13-23) run from the LIVE reference on seeded inputs."""
+    from . import eval_oracle
+    ev = ref_import.load_eval_modules()
+    V, J = 512, 44
+    kl = list(range(25, 39))                       # the 14 LSP joints (datasets_eval.yaml KEYPOINT_LIST)
+    out, batch = eval_oracle.synthetic_eval_batch(6, V=V, J=J, seed=11)
+    clone = lambda d: {k: (v.clone() if torch.is_tensor(v) else list(v)) for k, v in d.items()}
+    e1 = ev.pose_utils.Evaluator(dataset_length=16, keypoint_list=kl, pelvis_ind=39,
+                                 metrics=['mode_re', 'mode_mpjpe', 'mode_pve'], dataset='3DPW-TEST')
+    e1(clone(out), clone(batch))
+    g = torch.Generator().manual_seed(12)
+    jreg = torch.rand(24, V, generator=g) * (torch.rand(24, V, generator=g) < 0.06)
+    jreg = jreg / jreg.sum(-1, keepdim=True)
+    e2 = ev.pose_utils.Evaluator(dataset_length=16, keypoint_list=list(range(24)), pelvis_ind=39,
+                                 metrics=['mode_re', 'mode_mpjpe', 'mode_pve'], J_regressor_24_SMPL=jreg, dataset='EMDB')
+    e2(clone(out), clone(batch))
+    cam = torch.cat([0.6 + 0.5 * torch.rand(6, 1, generator=g), 0.2 * torch.randn(6, 2, generator=g)], -1)
+    center = torch.rand(6, 2, generator=g) * torch.tensor([1920., 1080.])
+    size = 150 + 400 * torch.rand(6, generator=g)
+    img_size = torch.tensor([[1920., 1080.]]).repeat(6, 1)
+    full = ev.renderer.cam_crop_to_full(cam, center, size, img_size, 5000. / 256 * img_size.max(dim=1)[0])
+    full_const = ev.renderer.cam_crop_to_full(cam, center, size, img_size)
+    np.savez_compressed(
+        GOLDEN / "evaluator.npz", meta=np.array([6, V, J, 11], np.int64), keypoint_list=np.array(kl, np.int32),
+        pred_vertices=out["pred_vertices"].numpy(), pred_keypoints_3d=out["pred_keypoints_3d"].numpy(),
+        gt_vertices=batch["vertices"].numpy(), gt_keypoints_3d=batch["keypoints_3d"].numpy(),
+        mpjpe=e1.mode_mpjpe[:6].astype(np.float32), re=e1.mode_re[:6].astype(np.float32),
+        pve=e1.mode_pve[:6].astype(np.float32), jreg=jreg.numpy(), emdb_mpjpe=e2.mode_mpjpe[:6].astype(np.float32),
+        emdb_re=e2.mode_re[:6].astype(np.float32), emdb_pve=e2.mode_pve[:6].astype(np.float32),
+        cam=cam.numpy(), center=center.numpy(), size=size.numpy(), img_size=img_size.numpy(),
+        full_cam_scaled=full.numpy(), full_cam=full_const.numpy())
+    print("wrote evaluator golden")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--release", action="store_true")
+    ap.add_argument("--only", default="", help="'eval': write only tests/golden/evaluator.npz")
     args = ap.parse_args()
     torch.set_num_threads(max(1, torch.get_num_threads()))
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    if args.only == "eval":
+        eval_goldens()
+        return
     ns = ref_import.load_modules()
     stage_goldens(ns)
+    eval_goldens()
     forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
     if args.release:
         forward_golden(ns, release_config(), 2, "forward_release_d32.npz")

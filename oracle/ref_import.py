@@ -106,6 +106,34 @@ def load_modules() -> types.SimpleNamespace:
     return ns
 
 
+def load_eval_modules() -> types.SimpleNamespace:
+    """The reference's evaluation helpers: lib/utils/pose_utils.py (imports cleanly: cv2 + torch) and
+    lib/utils/renderer.py for cam_crop_to_full (module-level imports of pyrender / trimesh / yacs are stubbed; the
+    function itself is plain torch, renderer.py:13-23)."""
+    load_modules()
+    class _Anything(types.ModuleType):   # annotations such as List[pyrender.Node] are evaluated at import
+        def __getattr__(self, k):
+            return type(k, (), {})
+
+    for name in ("pyrender", "trimesh"):
+        if name not in sys.modules:
+            sys.modules[name] = _Anything(name)
+    if "yacs" not in sys.modules:
+        yacs, yc = types.ModuleType("yacs"), types.ModuleType("yacs.config")
+        yc.CfgNode = dict
+        yacs.config = yc
+        sys.modules.update({"yacs": yacs, "yacs.config": yc})
+    ns = types.SimpleNamespace()
+    ns.pose_utils = importlib.import_module("lib.utils.pose_utils")
+    prev = os.environ.get("PYOPENGL_PLATFORM")
+    ns.renderer = importlib.import_module("lib.utils.renderer")   # sets PYOPENGL_PLATFORM at import
+    if prev is None:
+        os.environ.pop("PYOPENGL_PLATFORM", None)
+    else:
+        os.environ["PYOPENGL_PLATFORM"] = prev
+    return ns
+
+
 class _Cfg(dict):
     """Duck-typed stand-in for the yacs CfgNode the reference constructors read (attribute + .get access)."""
 

@@ -105,3 +105,60 @@ def test_fp16_emulation_stays_close_to_fp32():
         b = O.forward(sd, smpl, img, cfg, emulate_fp16=True)
     err = ((a["pred_vertices"] - b["pred_vertices"]).abs().max() / a["pred_vertices"].abs().max()).item()
     assert 0 < err < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ evaluation (f1/f3)
+def _eval_golden(golden_dir):
+    g = np.load(golden_dir / "evaluator.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    out = {"pred_vertices": t("pred_vertices"), "pred_keypoints_3d": t("pred_keypoints_3d")}
+    batch = {"vertices": t("gt_vertices"), "keypoints_3d": t("gt_keypoints_3d"), "imgname": ["x"] * 6}
+    return g, out, batch
+
+
+def test_evaluator_restatement_matches_reference_golden(golden_dir):
+    from oracle import eval_oracle as E
+    g, out, batch = _eval_golden(golden_dir)
+    m, r, p = E.evaluate_batch(out, batch, list(g["keypoint_list"]), 39)
+    for got, key in ((m, "mpjpe"), (r, "re"), (p, "pve")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=1e-3)
+    jreg = torch.from_numpy(g["jreg"])
+    m, r, p = E.evaluate_batch(out, batch, list(range(24)), 39, jreg, "EMDB")
+    for got, key in ((m, "emdb_mpjpe"), (r, "emdb_re"), (p, "emdb_pve")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=1e-3)
+    t = lambda k: torch.from_numpy(g[k])
+    np.testing.assert_allclose(E.cam_crop_to_full(t("cam"), t("center"), t("size"), t("img_size")).numpy(),
+                               g["full_cam"], rtol=1e-6, atol=1e-6)
+
+
+def test_evaluator_restatement_equals_live_reference():
+    if not ref_import.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle import eval_oracle as E
+    ev = ref_import.load_eval_modules()
+    kl = list(range(25, 39))
+    for seed in (0, 5):
+        out, batch = E.synthetic_eval_batch(5, V=300, seed=seed)
+        ref = ev.pose_utils.Evaluator(dataset_length=8, keypoint_list=kl, pelvis_ind=39,
+                                      metrics=['mode_re', 'mode_mpjpe', 'mode_pve'], dataset='3DPW-TEST')
+        ref({k: v.clone() for k, v in out.items()}, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+        m, r, p = E.evaluate_batch(out, batch, kl, 39)
+        np.testing.assert_allclose(m.numpy(), ref.mode_mpjpe[:5], rtol=1e-6)
+        np.testing.assert_allclose(r.numpy(), ref.mode_re[:5], rtol=1e-5)
+        np.testing.assert_allclose(p.numpy(), ref.mode_pve[:5], rtol=1e-6)
+        S1, S2 = out["pred_keypoints_3d"], batch["keypoints_3d"][..., :3]
+        torch.testing.assert_close(E.compute_similarity_transform(S1, S2),
+                                   ev.pose_utils.compute_similarity_transform(S1, S2), rtol=1e-5, atol=1e-5)
+
+
+def test_procrustes_known_answers():
+    """A similarity-transformed copy aligns back exactly; a reflected copy must NOT be matched by a reflection."""
+    from oracle import eval_oracle as E
+    g = torch.Generator().manual_seed(1)
+    S2 = torch.randn(3, 14, 3, generator=g)
+    c, s = np.cos(0.7), np.sin(0.7)
+    R = torch.tensor([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]], dtype=torch.float32)
+    S1 = 1.7 * S2 @ R.T + torch.tensor([0.3, -0.2, 0.9])
+    assert E.reconstruction_error(S1, S2).max() < 1e-5
+    mirrored = S2 * torch.tensor([1., 1., -1.])
+    assert E.reconstruction_error(mirrored, S2).min() > 0.1

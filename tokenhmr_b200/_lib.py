@@ -112,6 +112,10 @@ SIGNATURES = {
     "thmr_vq_dequantize": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "thmr_vq_dequant_logits": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "thmr_rot6d_to_rotmat": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "thmr_regress_joints": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "thmr_eval_pose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "thmr_cam_crop_to_full": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "thmr_smpl_create": (c_int, [POINTER(SmplDesc), POINTER(c_void_p)]),
     "thmr_smpl_destroy": (None, [c_void_p]),
     "thmr_smpl_workspace_bytes": (c_size_t, [c_void_p, c_int]),

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "engine.cuh"
+#include "eval_kernels.cuh"
 
 using namespace thmr;
 
@@ -154,6 +155,41 @@ int thmr_vq_dequant_logits(const void* logits16, int64_t Q, int K, const void* c
 int thmr_rot6d_to_rotmat(const float* x6, int64_t N, float* rot, void* stream) {
   THMR_CHECK(x6 && rot, "rot6d: null argument");
   rot6d_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(x6, rot, N);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ evaluation
+int thmr_regress_joints(const float* jreg, int J, const float* verts, int V, int B, float* joints, void* stream) {
+  THMR_CHECK(jreg && verts && joints, "regress_joints: null argument");
+  THMR_CHECK(J > 0 && V > 0 && B > 0, "regress_joints: bad shape J=%d V=%d B=%d", J, V, B);
+  regress_joints_kernel<<<B * J, 256, 0, static_cast<cudaStream_t>(stream)>>>(jreg, verts, joints, J, V);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+int thmr_eval_pose(const float* pred_kp, const float* gt_kp, int gt_stride, int J, const int32_t* keypoint_list, int K,
+                   int pelvis_a, int pelvis_b, const float* pred_verts, const float* gt_verts, int V, int B,
+                   float* mpjpe, float* re, float* pve, void* stream) {
+  THMR_CHECK(pred_kp && gt_kp && keypoint_list && mpjpe && re, "eval_pose: null argument");
+  THMR_CHECK(B > 0 && J > 0 && K > 0 && K <= kEvalMaxKp, "eval_pose: bad shape B=%d J=%d K=%d (K <= %d)", B, J, K,
+             kEvalMaxKp);
+  THMR_CHECK(gt_stride == 3 || gt_stride == 4, "eval_pose: gt_stride %d (3 or 4)", gt_stride);
+  THMR_CHECK(pelvis_a >= 0 && pelvis_a < J && pelvis_b >= 0 && pelvis_b < J, "eval_pose: pelvis index out of range");
+  THMR_CHECK(pve == nullptr || (pred_verts && gt_verts && V > 0), "eval_pose: pve needs both vertex sets");
+  eval_pose_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred_kp, gt_kp, gt_stride, J, keypoint_list, K,
+                                                                     pelvis_a, pelvis_b, pred_verts, gt_verts, V, mpjpe,
+                                                                     re, pve);
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+int thmr_cam_crop_to_full(const float* cam, const float* box_center, const float* box_size, const float* img_size,
+                          float focal_length, int B, float* full_cam, void* stream) {
+  THMR_CHECK(cam && box_center && box_size && img_size && full_cam, "cam_crop_to_full: null argument");
+  THMR_CHECK(B > 0, "cam_crop_to_full: bad batch %d", B);
+  cam_crop_to_full_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(cam, box_center, box_size,
+                                                                                       img_size, focal_length, full_cam, B);
   THMR_CUDA(cudaGetLastError());
   return THMR_OK;
 }

@@ -127,6 +127,63 @@ def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------ evaluation
+def regress_joints(jreg: torch.Tensor, verts: torch.Tensor) -> torch.Tensor:
+    """torch.matmul(J_regressor, vertices) (tokenhmr/lib/utils/pose_utils.py:213,219): (J,V) x (B,V,3) -> (B,J,3)."""
+    jreg = _req(jreg, torch.float32, "jreg")
+    verts = _req(verts, torch.float32, "verts")
+    if jreg.dim() != 2 or verts.dim() != 3 or verts.shape[1] != jreg.shape[1] or verts.shape[2] != 3:
+        raise ValueError(f"regress_joints: jreg {tuple(jreg.shape)} vs verts {tuple(verts.shape)}")
+    out = torch.empty(verts.shape[0], jreg.shape[0], 3, device=verts.device, dtype=torch.float32)
+    check(lib().thmr_regress_joints(jreg.data_ptr(), jreg.shape[0], verts.data_ptr(), verts.shape[1], verts.shape[0],
+                                    out.data_ptr(), _stream()))
+    return out
+
+
+def eval_pose(pred_kp: torch.Tensor, gt_kp: torch.Tensor, keypoint_list: torch.Tensor, pelvis: Tuple[int, int],
+              pred_verts: Optional[torch.Tensor] = None, gt_verts: Optional[torch.Tensor] = None):
+    """Pelvis alignment + MPJPE + Procrustes-aligned MPJPE (+ PVE) in mm for one batch
+    (tokenhmr/lib/utils/pose_utils.py:61-143,201-275).  gt_kp may still carry the confidence column (B,J,4).
+    Returns (mpjpe, re, pve-or-None), each (B,) fp32 on the GPU."""
+    pred_kp = _req(pred_kp, torch.float32, "pred_kp")
+    gt_kp = _req(gt_kp, torch.float32, "gt_kp")
+    keypoint_list = _req(keypoint_list, torch.int32, "keypoint_list")
+    B, J = pred_kp.shape[0], pred_kp.shape[1]
+    if pred_kp.dim() != 3 or pred_kp.shape[2] != 3 or gt_kp.dim() != 3 or gt_kp.shape[:2] != pred_kp.shape[:2] \
+            or gt_kp.shape[2] not in (3, 4):
+        raise ValueError(f"eval_pose: pred_kp {tuple(pred_kp.shape)} vs gt_kp {tuple(gt_kp.shape)}")
+    mpjpe = torch.empty(B, device=pred_kp.device, dtype=torch.float32)
+    re = torch.empty_like(mpjpe)
+    pve, pv, gv, V = None, 0, 0, 0
+    if pred_verts is not None or gt_verts is not None:
+        pred_verts = _req(pred_verts, torch.float32, "pred_verts")
+        gt_verts = _req(gt_verts, torch.float32, "gt_verts")
+        if pred_verts.shape != gt_verts.shape or pred_verts.shape[0] != B or pred_verts.shape[-1] != 3:
+            raise ValueError(f"eval_pose: vertices {tuple(pred_verts.shape)} vs {tuple(gt_verts.shape)}")
+        pve = torch.empty_like(mpjpe)
+        pv, gv, V = pred_verts.data_ptr(), gt_verts.data_ptr(), pred_verts.shape[1]
+    check(lib().thmr_eval_pose(pred_kp.data_ptr(), gt_kp.data_ptr(), gt_kp.shape[2], J, keypoint_list.data_ptr(),
+                               keypoint_list.numel(), int(pelvis[0]), int(pelvis[1]), pv, gv, V, B, mpjpe.data_ptr(),
+                               re.data_ptr(), pve.data_ptr() if pve is not None else 0, _stream()))
+    return mpjpe, re, pve
+
+
+def cam_crop_to_full(cam_bbox: torch.Tensor, box_center: torch.Tensor, box_size: torch.Tensor, img_size: torch.Tensor,
+                     focal_length: float = 5000.0) -> torch.Tensor:
+    """tokenhmr/lib/utils/renderer.py:13-23 (same argument order)."""
+    cam_bbox = _req(cam_bbox, torch.float32, "cam_bbox")
+    box_center = _req(box_center, torch.float32, "box_center")
+    box_size = _req(box_size.reshape(-1), torch.float32, "box_size")
+    img_size = _req(img_size, torch.float32, "img_size")
+    B = cam_bbox.shape[0]
+    if cam_bbox.shape != (B, 3) or box_center.shape != (B, 2) or box_size.shape != (B,) or img_size.shape != (B, 2):
+        raise ValueError("cam_crop_to_full: expected cam (B,3), center (B,2), size (B,), img_size (B,2)")
+    out = torch.empty(B, 3, device=cam_bbox.device, dtype=torch.float32)
+    check(lib().thmr_cam_crop_to_full(cam_bbox.data_ptr(), box_center.data_ptr(), box_size.data_ptr(),
+                                      img_size.data_ptr(), float(focal_length), B, out.data_ptr(), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ SMPL
 class SMPLModel:
     """Device-resident SMPL model (thmr_smpl).  `smpl` holds the smplx buffers: v_template, shapedirs, posedirs,
