@@ -112,6 +112,37 @@ int thmr_cam_crop_to_full(const float* cam, const float* box_center, const float
                           float focal_length, int B, float* full_cam, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input pre-processing (the step before the path)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thmr_preproc_cfg {
+  int image_size;          /* MODEL.IMAGE_SIZE: 256 */
+  int bbox_w, bbox_h;      /* MODEL.BBOX_SHAPE: 192, 256 (0, 0 = None) */
+  double mean[3], std[3];  /* MODEL.IMAGE_MEAN / IMAGE_STD, RGB order, 0..1 scale (multiplied by 255 inside) */
+} thmr_preproc_cfg;
+
+/* ViTDetDataset.__init__ / __getitem__ for all boxes of one frame
+ * [tokenhmr/lib/datasets/vitdet_dataset.py:17-88 -> utils.py:14-33 (expand_to_aspect_ratio), :81-129
+ * (gen_trans_from_patch_cv), :317-361 (generate_image_patch_cv2), :364-376 (convert_cvimg_to_tensor)]:
+ *   img_bgr     uint8 [H, pitch_bytes] device, BGR interleaved as cv2.imread returns it;
+ *   boxes_host  fp32 [n,4] (x0,y0,x1,y1) HOST (the detector's boxes, demo.py:64-70);
+ *   out_img     fp32 [n,3,S,S] device = batch['img'] (RGB, (v - 255 mean) / (255 std));
+ *   out_patch_u8 (nullable) uint8 [n,S,S,3] device: the BGR crop cv2.warpAffine returns (8-bit path only; bit exact);
+ *   box_center_host [n,2], box_size_host [n], sigma_host [n] (each nullable, HOST): the item's 'box_center',
+ *   'box_size' and the anti-alias sigma that was applied (0 = none).
+ * Boxes wider than 2.2 * S pixels take the blurred path (Gaussian over the box's source region, then the remap on
+ * fp32 data); the others are bit exact with cv2's 8-bit remap.  Stream-ordered; one pageable H2D copy of the
+ * per-person parameters, so not graph-capturable.  workspace: thmr_preprocess_workspace_bytes(H, W, n) bytes. */
+size_t thmr_preprocess_workspace_bytes(int img_h, int img_w, int n);
+/* The host half alone (no CUDA call): 'box_center' [n,2], 'box_size' [n], blur sigma [n] and the inverse affine
+ * map cv2.warpAffine derives from gen_trans_from_patch_cv's matrix, [n,6] doubles (each output nullable). */
+int thmr_preprocess_plan(const float* boxes_host, int n, const thmr_preproc_cfg* cfg, float* box_center_host,
+                         float* box_size_host, float* sigma_host, double* inv_affine_host);
+int thmr_preprocess_boxes(const uint8_t* img_bgr, int img_h, int img_w, int64_t pitch_bytes, const float* boxes_host,
+                          int n, const thmr_preproc_cfg* cfg, float* out_img, uint8_t* out_patch_u8,
+                          float* box_center_host, float* box_size_host, float* sigma_host, void* workspace,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SMPL body model (smplx==0.1.28 SMPLLayer / lbs, wrapped by tokenhmr/lib/models/smpl_wrapper.py:10-41)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thmr_smpl thmr_smpl;

@@ -128,6 +128,44 @@ def eval_goldens() -> None:
     print("wrote evaluator golden")
 
 
+def preproc_scene(seed: int = 21, H: int = 208, W: int = 272):
+    """Small synthetic BGR frame (smooth structure + noise) and person boxes that cover every branch of
+    ViTDetDataset.__getitem__: interior box, boxes crossing the frame border, a wide box (aspect-ratio expansion
+    on the other side) and two boxes wider than 2.2 x 256 px (anti-alias blur, sigma 0.60 and 1.46)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 127 + 70 * np.sin(xx / 9.0)[..., None] * np.cos(yy / 13.0)[..., None] * np.array([1.0, 0.6, -0.8])
+    img = (base + rng.normal(0, 18, (H, W, 3))).clip(0, 255).astype(np.uint8)
+    boxes = np.array([[60.3, 20.2, 180.7, 190.9], [-40.0, -30.0, 120.0, 150.0], [150.5, 100.25, 300.0, 230.0],
+                      [20.0, 80.0, 250.0, 130.0], [-250.0, -300.0, 520.0, 540.0], [-900.0, -700.0, 1100.0, 1000.0]],
+                     np.float32)
+    return img, boxes
+
+
+def preproc_goldens() -> None:
+    """ViTDetDataset items (vitdet_dataset.py:44-88) from the LIVE reference class, cv2 4.x + scipy real,
+    skimage.filters.gaussian shimmed onto scipy.ndimage (ref_import.load_dataset_modules)."""
+    ds_mod = ref_import.load_dataset_modules()
+    img, boxes = preproc_scene()
+    ds = ds_mod.vitdet_dataset.ViTDetDataset(ref_import.dataset_cfg(), img, boxes)
+    items = [ds[i] for i in range(len(boxes))]
+    imgs = np.stack([it["img"] for it in items]).astype(np.float32)
+    # the 8-bit crops are stored as bytes (the float image is a table lookup of them); blurred crops as float16-safe
+    # float32 planes
+    m = 255.0 * np.array([0.485, 0.456, 0.406]); s = 255.0 * np.array([0.229, 0.224, 0.225])
+    u8 = np.stack([np.rint(imgs[i] * s[:, None, None] + m[:, None, None]).clip(0, 255).astype(np.uint8) for i in range(len(items))])
+    is_u8 = np.array([np.array_equal(((u8[i].astype(np.float64) - m[:, None, None]) / s[:, None, None]).astype(np.float32),
+                                     imgs[i]) for i in range(len(items))])
+    np.savez_compressed(
+        GOLDEN / "preproc.npz", meta=np.array([21, img.shape[0], img.shape[1]], np.int64), boxes=boxes,
+        box_center=np.stack([it["box_center"] for it in items]).astype(np.float32),
+        box_size=np.array([it["box_size"] for it in items], np.float32),
+        img_size=np.stack([it["img_size"] for it in items]),
+        is_u8=is_u8, rgb_u8=u8[is_u8], img_blur=imgs[~is_u8],
+        cv2_version=np.array(__import__("cv2").__version__), numpy_version=np.array(np.__version__))
+    print("wrote preproc golden:", int(is_u8.sum()), "8-bit crops,", int((~is_u8).sum()), "blurred crops")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--release", action="store_true")
@@ -137,6 +175,9 @@ def main() -> None:
     GOLDEN.mkdir(parents=True, exist_ok=True)
     if args.only == "eval":
         eval_goldens()
+        return
+    if args.only == "preproc":
+        preproc_goldens()
         return
     ns = ref_import.load_modules()
     stage_goldens(ns)

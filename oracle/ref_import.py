@@ -134,6 +134,48 @@ def load_eval_modules() -> types.SimpleNamespace:
     return ns
 
 
+def load_dataset_modules() -> types.SimpleNamespace:
+    """The reference's inference pre-processing: lib/datasets/vitdet_dataset.py and lib/datasets/utils.py (SURVEY
+    §8 row f2).  cv2 and scipy are real here; skimage is absent, so `skimage.filters.gaussian` is a shim that does
+    what skimage itself does for this call (uint8 -> float64 with preserve_range, scipy.ndimage.gaussian_filter
+    over the image axes, mode 'nearest', truncate 4.0); `skimage.transform.rotate/resize` (training-only crop
+    path, utils.py:6) and yacs.config.CfgNode (annotation only) are stubbed."""
+    load_modules()
+    if "skimage" not in sys.modules:
+        import scipy.ndimage as ndi
+        sk, skf, skt = types.ModuleType("skimage"), types.ModuleType("skimage.filters"), types.ModuleType("skimage.transform")
+
+        def gaussian(image, sigma=1, *, mode="nearest", cval=0, preserve_range=False, truncate=4.0, channel_axis=None):
+            assert preserve_range and channel_axis is not None, "only the vitdet_dataset.py:66 call is shimmed"
+            img = image if image.dtype.char in "df" else image.astype(float)
+            sig = [float(sigma)] * img.ndim
+            sig[channel_axis] = 0.0
+            return ndi.gaussian_filter(img, sig, mode=mode, cval=cval, truncate=truncate)
+
+        def _unused(*a, **k):
+            raise RuntimeError("skimage.transform is outside the inference path")
+
+        skf.gaussian, skt.rotate, skt.resize = gaussian, _unused, _unused
+        sk.filters, sk.transform = skf, skt
+        sys.modules.update({"skimage": sk, "skimage.filters": skf, "skimage.transform": skt})
+    if "yacs" not in sys.modules:
+        yacs, yc = types.ModuleType("yacs"), types.ModuleType("yacs.config")
+        yc.CfgNode = dict
+        yacs.config = yc
+        sys.modules.update({"yacs": yacs, "yacs.config": yc})
+    _namespace("lib.datasets", REF_ROOT / "tokenhmr" / "lib" / "datasets")
+    ns = types.SimpleNamespace()
+    ns.utils = importlib.import_module("lib.datasets.utils")
+    ns.vitdet_dataset = importlib.import_module("lib.datasets.vitdet_dataset")
+    return ns
+
+
+def dataset_cfg(image_size: int = 256, bbox_shape=(192, 256)):
+    """The MODEL keys ViTDetDataset reads (vitdet_dataset.py:31-33,52); values of the release model_config.yaml."""
+    return _Cfg({"MODEL": {"IMAGE_SIZE": image_size, "IMAGE_MEAN": [0.485, 0.456, 0.406],
+                           "IMAGE_STD": [0.229, 0.224, 0.225], "BBOX_SHAPE": list(bbox_shape) if bbox_shape else None}})
+
+
 class _Cfg(dict):
     """Duck-typed stand-in for the yacs CfgNode the reference constructors read (attribute + .get access)."""
 

@@ -71,6 +71,11 @@ class Weights(Structure):
                 ("res_conv1", Conv * 8), ("res_conv2", Conv * 8), ("conv_post", Conv), ("conv_out", Conv)]
 
 
+class PreprocCfg(Structure):
+    _fields_ = [("image_size", c_int), ("bbox_w", c_int), ("bbox_h", c_int),
+                ("mean", ctypes.c_double * 3), ("std", ctypes.c_double * 3)]
+
+
 class Outputs(Structure):
     _fields_ = [(n, c_void_p) for n in ("cls_logits_softmax", "pred_cam", "rotmats", "betas", "pred_cam_t",
                                         "focal_length", "pred_keypoints_3d", "pred_vertices", "pred_keypoints_2d",
@@ -116,6 +121,10 @@ SIGNATURES = {
     "thmr_eval_pose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "thmr_cam_crop_to_full": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "thmr_preprocess_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "thmr_preprocess_plan": (c_int, [c_void_p, c_int, POINTER(PreprocCfg), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "thmr_preprocess_boxes": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, POINTER(PreprocCfg), c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "thmr_smpl_create": (c_int, [POINTER(SmplDesc), POINTER(c_void_p)]),
     "thmr_smpl_destroy": (None, [c_void_p]),
     "thmr_smpl_workspace_bytes": (c_size_t, [c_void_p, c_int]),

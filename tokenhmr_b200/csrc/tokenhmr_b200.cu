@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "engine.cuh"
 #include "eval_kernels.cuh"
+#include "preproc.cuh"
 
 using namespace thmr;
 
@@ -34,7 +35,7 @@ int dev_clone(T** p, const T* src, size_t n) {
 
 extern "C" {
 
-int thmr_abi_version(void) { return 2; }
+int thmr_abi_version(void) { return 3; }
 
 const char* thmr_last_error(void) { return last_error_buf(); }
 
@@ -191,6 +192,144 @@ int thmr_cam_crop_to_full(const float* cam, const float* box_center, const float
   cam_crop_to_full_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(cam, box_center, box_size,
                                                                                        img_size, focal_length, full_cam, B);
   THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pre-processing
+size_t thmr_preprocess_workspace_bytes(int img_h, int img_w, int n) {
+  if (img_h <= 0 || img_w <= 0 || n < 0) return 0;
+  return pre_layout(img_h, img_w, n).total + 256;
+}
+
+// Host half of the pre-processing (no CUDA call): box -> centre / size / blur sigma / inverse affine map, in float32
+// and double exactly as the reference computes them.
+int thmr_preprocess_plan(const float* boxes_host, int n, const thmr_preproc_cfg* cfg, float* box_center_host,
+                         float* box_size_host, float* sigma_host, double* inv_affine_host) {
+  THMR_CHECK(boxes_host && cfg, "preprocess_plan: null argument");
+  THMR_CHECK(n > 0, "preprocess_plan: no boxes");
+  const int S = cfg->image_size;
+  THMR_CHECK(S >= 16 && S <= 4096, "preprocess_plan: image_size %d", S);
+  for (int i = 0; i < n; ++i) {
+    const float* b = boxes_host + 4 * i;
+    THMR_CHECK(b[2] > b[0] && b[3] > b[1], "preprocess: box %d is empty (%g,%g,%g,%g)", i, b[0], b[1], b[2], b[3]);
+    volatile float sx_ = b[2] + b[0], sy_ = b[3] + b[1];
+    const float cx = sx_ / 2.0f, cy = sy_ / 2.0f;
+    volatile float dw = b[2] - b[0], dh = b[3] - b[1];
+    volatile float sw = dw / 200.0f, sh = dh / 200.0f;           // self.scale
+    volatile float w = sw * 200.0f, h = sh * 200.0f;             // scale * 200
+    const float bsz = pre_bbox_size(w, h, cfg->bbox_w, cfg->bbox_h);
+    if (box_center_host) { box_center_host[2 * i] = cx; box_center_host[2 * i + 1] = cy; }
+    if (box_size_host) box_size_host[i] = bsz;
+    volatile float f1 = bsz / static_cast<float>(S);
+    volatile float f = f1 / 2.0f;
+    float sigma = 0.f;
+    if (f > 1.1f) {
+      volatile float t = f - 1.0f;
+      sigma = t / 2.0f;
+    }
+    if (sigma_host) sigma_host[i] = sigma;
+    if (inv_affine_host) {
+      // gen_trans_from_patch_cv (utils.py:81-129), scale 1, rot 0
+      volatile float half = bsz * 0.5f;
+      float src[3][2], dst[3][2];
+      src[0][0] = cx; src[0][1] = cy;
+      src[1][0] = cx; src[1][1] = static_cast<float>(static_cast<double>(cy) + static_cast<double>(half));
+      src[2][0] = static_cast<float>(static_cast<double>(cx) + static_cast<double>(half)); src[2][1] = cy;
+      const float hs = static_cast<float>(S * 0.5);
+      dst[0][0] = hs; dst[0][1] = hs; dst[1][0] = hs; dst[1][1] = hs + hs; dst[2][0] = hs + hs; dst[2][1] = hs;
+      double M[6];
+      THMR_CHECK(pre_get_affine(src, dst, M), "preprocess: box %d gives a singular transform", i);
+      pre_invert_affine(M, inv_affine_host + 6 * i);
+    }
+  }
+  return THMR_OK;
+}
+
+int thmr_preprocess_boxes(const uint8_t* img_bgr, int img_h, int img_w, int64_t pitch_bytes, const float* boxes_host,
+                          int n, const thmr_preproc_cfg* cfg, float* out_img, uint8_t* out_patch_u8,
+                          float* box_center_host, float* box_size_host, float* sigma_host, void* workspace,
+                          void* stream) {
+  THMR_CHECK(img_bgr && boxes_host && cfg && out_img && workspace, "preprocess: null argument");
+  THMR_CHECK(img_h > 1 && img_w > 1 && pitch_bytes >= 3LL * img_w, "preprocess: bad image %dx%d pitch %lld", img_h,
+             img_w, static_cast<long long>(pitch_bytes));
+  THMR_CHECK(n > 0, "preprocess: no boxes");
+  const int S = cfg->image_size;
+  for (int c = 0; c < 3; ++c) THMR_CHECK(cfg->std[c] > 0, "preprocess: std[%d] must be positive", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  const PreLayout L = pre_layout(img_h, img_w, n);
+
+  std::vector<uint8_t> blob(L.tmp_off, 0);
+  PrePerson* persons = reinterpret_cast<PrePerson*>(blob.data() + L.persons_off);
+  int* which = reinterpret_cast<int*>(blob.data() + L.which_off);
+  float* lut = reinterpret_cast<float*>(blob.data() + L.lut_off);
+  double* wts = reinterpret_cast<double*>(blob.data() + L.wts_off);
+  double mean[3], sd[3];                                         // RGB order, 0..255 scale (vitdet_dataset.py:32-33)
+  for (int c = 0; c < 3; ++c) { mean[c] = 255.0 * cfg->mean[c]; sd[c] = 255.0 * cfg->std[c]; }
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) lut[c * 256 + v] = static_cast<float>((static_cast<double>(v) - mean[c]) / sd[c]);
+  std::vector<float> sigma(n, 0.f), size(n);
+  std::vector<double> inv(6 * static_cast<size_t>(n));
+  std::vector<int> radius(n, 0);
+  THMR_TRY(thmr_preprocess_plan(boxes_host, n, cfg, box_center_host, size.data(), sigma.data(), inv.data()));
+  int n_u8 = 0;
+  for (int i = 0; i < n; ++i) {
+    if (box_size_host) box_size_host[i] = size[i];
+    if (sigma_host) sigma_host[i] = sigma[i];
+    memcpy(persons[i].iM, &inv[6 * static_cast<size_t>(i)], sizeof(double) * 6);
+    if (sigma[i] > 0.f) {
+      const double sg = static_cast<double>(sigma[i]);
+      const int r = static_cast<int>(4.0 * sg + 0.5);
+      THMR_CHECK(2 * r + 1 <= kPreMaxTaps, "preprocess: box %d needs a %d-tap blur (max %d)", i, 2 * r + 1, kPreMaxTaps);
+      radius[i] = r;
+      double* wi = wts + static_cast<size_t>(i) * kPreMaxTaps;
+      double sum = 0;
+      for (int k = -r; k <= r; ++k) { wi[k + r] = exp(-0.5 / (sg * sg) * static_cast<double>(k * k)); sum += wi[k + r]; }
+      for (int k = 0; k <= 2 * r; ++k) wi[k] /= sum;
+    } else {
+      which[n_u8++] = i;
+    }
+  }
+  THMR_CUDA(cudaMemcpyAsync(ws, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+  const PrePerson* d_persons = reinterpret_cast<const PrePerson*>(ws + L.persons_off);
+  const int* d_which = reinterpret_cast<const int*>(ws + L.which_off);
+  const float* d_lut = reinterpret_cast<const float*>(ws + L.lut_off);
+  const double* d_wts = reinterpret_cast<const double*>(ws + L.wts_off);
+  float* tmp = reinterpret_cast<float*>(ws + L.tmp_off);
+  float* blur = reinterpret_cast<float*>(ws + L.blur_off);
+  const int px_blocks = (S * S + 255) / 256;
+  if (n_u8 > 0) {
+    preproc_warp_u8_kernel<<<dim3(px_blocks, n_u8), 256, 0, st>>>(img_bgr, img_h, img_w, pitch_bytes, d_persons, d_which,
+                                                                 d_lut, S, out_img, out_patch_u8);
+    THMR_CUDA(cudaGetLastError());
+  }
+  for (int i = 0; i < n; ++i) {
+    if (sigma[i] <= 0.f) continue;
+    // source region the remap can touch: the box (+2 px for the bilinear footprint and rounding), clipped
+    const double half = 0.5 * static_cast<double>(size[i]);
+    const double cx = 0.5 * (static_cast<double>(boxes_host[4 * i]) + boxes_host[4 * i + 2]);
+    const double cy = 0.5 * (static_cast<double>(boxes_host[4 * i + 1]) + boxes_host[4 * i + 3]);
+    const int r = radius[i];
+    int x0 = static_cast<int>(floor(cx - half)) - 3, x1 = static_cast<int>(ceil(cx + half)) + 4;
+    int y0 = static_cast<int>(floor(cy - half)) - 3, y1 = static_cast<int>(ceil(cy + half)) + 4;
+    x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, img_w); y1 = std::min(y1, img_h);
+    if (x0 < x1 && y0 < y1) {
+      const int vx0 = std::max(x0 - r, 0), vx1 = std::min(x1 + r, img_w);    // the column pass reads +-r around x
+      const long long nv = 3LL * (vx1 - vx0) * (y1 - y0), nh = 3LL * (x1 - x0) * (y1 - y0);
+      const double* wi = d_wts + static_cast<size_t>(i) * kPreMaxTaps;
+      preproc_gauss_kernel<0><<<static_cast<unsigned>((nv + 255) / 256), 256, 0, st>>>(img_bgr, pitch_bytes, img_h, img_w,
+                                                                                     wi, r, vx0, vx1, y0, y1, tmp);
+      THMR_CUDA(cudaGetLastError());
+      preproc_gauss_kernel<1><<<static_cast<unsigned>((nh + 255) / 256), 256, 0, st>>>(tmp, 0, img_h, img_w, wi, r, x0, x1,
+                                                                                     y0, y1, blur);
+      THMR_CUDA(cudaGetLastError());
+    }
+    PrePerson pp;
+    memcpy(&pp, &persons[i], sizeof(pp));
+    preproc_warp_f32_kernel<<<px_blocks, 256, 0, st>>>(blur, img_h, img_w, pp, i, S, mean[0], mean[1], mean[2], sd[0],
+                                                       sd[1], sd[2], out_img);
+    THMR_CUDA(cudaGetLastError());
+  }
   return THMR_OK;
 }
 
