@@ -180,6 +180,35 @@ int thmr_smpl_forward(const thmr_smpl* m, const float* rotmats /* [B,24,3,3] */,
                       float* verts, float* joints, const float* pred_cam, float focal_length, float image_size,
                       float* cam_t, float* focal_out, float* kp2d, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tokenizer encoder + hard quantisation: EncodeTokens
+ * [tokenization/models/vanilla_pose_vqvae.py:304-346 -> PoseSPEncoderV1 :42-111, quantize_cnn.py:74-86]
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct thmr_tok_encoder thmr_tok_encoder;
+typedef struct thmr_tok_conv { const void* w; const float* b; } thmr_tok_conv;  /* f16 [Cout, taps*Cin] tap-major, fp32 bias */
+typedef struct thmr_tok_encoder_desc {
+  int joints, in_dim;              /* 21, 6 */
+  int width, depth, dilation_rate; /* ARCH.WIDTH 512, DEPTH 2, DILATION_RATE 3 */
+  int size_mul;                    /* ARCH.TOKEN_SIZE_MUL 4: Upsample(40) + (size_mul-1) x Upsample(x2) */
+  int code_dim, nb_code;           /* 256, 2048 */
+  thmr_tok_conv conv_in;           /* Conv1d(in_dim,W,3): [W, 3*64], the in_dim channels zero-padded to 64 per tap */
+  thmr_tok_conv conv_up[8];        /* the size_mul Conv1d(W,W,3) that follow the Upsample layers */
+  thmr_tok_conv conv_down;         /* Conv1d(W,W,4,stride 2,pad 1): [W, 4*W] */
+  thmr_tok_conv res_conv1[8], res_conv2[8]; /* Resnet1D blocks in stored order (dilation rate^(depth-1) ... 1) */
+  thmr_tok_conv conv_out;          /* Conv1d(W,code_dim,3) */
+  const float* codebook;           /* fp32 [nb_code, code_dim] */
+} thmr_tok_encoder_desc;
+
+/* The descriptor is copied; the weight buffers stay caller-owned and must outlive the encoder. */
+int thmr_tok_encoder_create(const thmr_tok_encoder_desc* desc, thmr_tok_encoder** out);
+void thmr_tok_encoder_destroy(thmr_tok_encoder* e);
+int thmr_tok_encoder_num_tokens(const thmr_tok_encoder* e);            /* T = 160 for the release tokenizer */
+size_t thmr_tok_encoder_workspace_bytes(const thmr_tok_encoder* e, int batch);
+/* EncodeTokens.forward: pose6d fp32 [B, joints, in_dim] -> code_idx int64 [B*T] (first minimum, as torch.min);
+ * latent (nullable) fp32 [B*T, code_dim] receives the encoder output the quantiser saw. */
+int thmr_tok_encode(const thmr_tok_encoder* e, const float* pose6d, int B, int64_t* code_idx, float* latent,
+                    void* workspace, void* stream);
+
 /* ================================================================================================
  * Engine: TokenHMR.forward(batch)  [tokenhmr.py:330-338 -> 135-188]
  * ============================================================================================== */

@@ -166,6 +166,33 @@ def preproc_goldens() -> None:
     print("wrote preproc golden:", int(is_u8.sum()), "8-bit crops,", int((~is_u8).sum()), "blurred crops")
 
 
+def encoder_goldens(ns) -> None:
+    """EncodeTokens.forward (vanilla_pose_vqvae.py:334-342) from the LIVE reference class on seeded 6D poses, with the
+    synthetic codebook and with a codebook drawn from the encoder's own latents (so that the indices are spread)."""
+    from tokenhmr_b200.config import release_config as rc
+    cfg = rc()
+    sd = synth.make_tokenizer_encoder_state_dict(cfg, 1234)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(6, cfg.tok_joints, 6, generator=g)
+    with torch.no_grad():
+        enc = ref_import.build_encode_tokens(ns, sd, cfg)
+        idx_a = enc(x)
+        lat = enc.quantizer.preprocess(enc.encoder(x))
+        # second codebook: latents of other poses + noise
+        xb = torch.randn(16, cfg.tok_joints, 6, generator=g)
+        lat_b = enc.quantizer.preprocess(enc.encoder(xb))
+        cb = lat_b[torch.randperm(lat_b.shape[0], generator=g)[:cfg.nb_code]] + 0.05 * torch.randn(cfg.nb_code, cfg.code_dim, generator=g)
+        cb = cb.half().float()                      # stored as fp16 (1 MB): the codebook IS these rounded values
+        sd2 = dict(sd)
+        sd2["tokenizer.quantizer.codebook"] = cb
+        enc2 = ref_import.build_encode_tokens(ns, sd2, cfg)
+        idx_b = enc2(x)
+    np.savez_compressed(GOLDEN / "tok_encoder.npz", meta=np.array([1234, 31, 6], np.int64), x=x.numpy(),
+                        idx_synth=idx_a.numpy().astype(np.int32), idx_latent_cb=idx_b.numpy().astype(np.int32),
+                        latent_sub=lat[::7].numpy(), codebook_latent=cb.numpy().astype(np.float16))
+    print("wrote tok_encoder golden:", idx_a.unique().numel(), "/", idx_b.unique().numel(), "distinct codes")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--release", action="store_true")
@@ -179,9 +206,14 @@ def main() -> None:
     if args.only == "preproc":
         preproc_goldens()
         return
+    if args.only == "encoder":
+        encoder_goldens(ref_import.load_modules())
+        return
     ns = ref_import.load_modules()
     stage_goldens(ns)
     eval_goldens()
+    preproc_goldens()
+    encoder_goldens(ns)
     forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
     if args.release:
         forward_golden(ns, release_config(), 2, "forward_release_d32.npz")

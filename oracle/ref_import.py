@@ -246,6 +246,27 @@ def build_head(ns, sd, cfg):
     return head
 
 
+def build_encode_tokens(ns, sd, cfg):
+    """EncodeTokens (vanilla_pose_vqvae.py:304-346) built by the reference constructor from a synthetic tokenizer
+    'checkpoint' ({'hparams', 'net'}); `sd` holds tokenizer.encoder.* and tokenizer.quantizer.codebook."""
+    tok_sd = {k[len("tokenizer."):]: v for k, v in sd.items()
+              if k.startswith(("tokenizer.encoder.", "tokenizer.quantizer."))}
+    arch = argparse.Namespace(ROT_TYPE="rot6d", CODE_DIM=cfg.code_dim, NB_CODE=cfg.nb_code, DOWN_T=1,
+                              WIDTH=cfg.tok_width, DEPTH=cfg.tok_depth, DILATION_RATE=cfg.tok_dilation_rate,
+                              TOKEN_SIZE_DIV=cfg.tok_size_div, TOKEN_SIZE_MUL=cfg.tok_size_mul)
+    fake_ckpt = {"hparams": argparse.Namespace(ARCH=arch), "net": tok_sd}
+    real_load = torch.load
+    torch.load = lambda *a, **k: fake_ckpt
+    import contextlib, io
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc = ns.vqvae.EncodeTokens("synthetic-tokenizer.pth")
+    finally:
+        torch.load = real_load
+    enc.eval()
+    return enc
+
+
 def reference_forward(ns, backbone, head, smpl, img, cfg):
     """TokenHMR.forward_step (tokenhmr.py:135-188) glue around the LIVE reference backbone / head / geometry;
     only the smplx call (tokenhmr.py:176) goes to the unpinned restatement in smpl_oracle."""

@@ -49,8 +49,8 @@ class Numerics:
     def matmul(self, a: Tensor, b: Tensor) -> Tensor:
         return torch.matmul(self.q(a), self.q(b))
 
-    def conv1d(self, x: Tensor, w: Tensor, b: Tensor, padding: int, dilation: int = 1) -> Tensor:
-        return F.conv1d(self.q(x), self.q(w), b, stride=1, padding=padding, dilation=dilation)
+    def conv1d(self, x: Tensor, w: Tensor, b: Tensor, padding: int, dilation: int = 1, stride: int = 1) -> Tensor:
+        return F.conv1d(self.q(x), self.q(w), b, stride=stride, padding=padding, dilation=dilation)
 
     def conv2d(self, x: Tensor, w: Tensor, b: Tensor, stride: int, padding: int) -> Tensor:
         return F.conv2d(self.q(x), self.q(w), b, stride=stride, padding=padding)
@@ -206,6 +206,34 @@ def tokenizer_decode(sd: Dict[str, Tensor], probs: Tensor, cfg, nm: Numerics,
     x = nm.conv1d(x, g(f"{t}{idx}.1.weight"), g(f"{t}{idx}.1.bias"), padding=1)
     x = nm.conv1d(x, g(f"{t}{idx + 1}.weight"), g(f"{t}{idx + 1}.bias"), padding=1)  # (B,6,21)
     return x.permute(0, 2, 1)                                                       # postprocess :156-159
+
+
+def tokenizer_encode(sd: Dict[str, Tensor], pose6d: Tensor, cfg, nm: Numerics, prefix: str = "tokenizer."):
+    """EncodeTokens.forward (vanilla_pose_vqvae.py:334-342): PoseSPEncoderV1 (:42-111: preprocess :88-92, the
+    Sequential built at :65-86 with Resnet1D reverse_dilation=True, resnet.py:70-82) + QuantizeEMAReset.preprocess /
+    quantize (quantize_cnn.py:74-86).  pose6d (B,21,6) -> (code_idx (B*T,) int64, latent (B*T, code_dim))."""
+    g = lambda n: sd[prefix + n]
+    e = "encoder.encoder."
+    B = pose6d.shape[0]
+    x = pose6d.reshape(B, pose6d.shape[1], -1).permute(0, 2, 1)                     # (B,6,21)
+    x = F.relu(nm.conv1d(x, g(e + "0.weight"), g(e + "0.bias"), padding=1))
+    x = x[:, :, upsample_nearest_index(((cfg.tok_joints * 2) // 10) * 10, x.shape[-1])]   # nn.Upsample(40), :69
+    x = F.relu(nm.conv1d(x, g(e + "3.weight"), g(e + "3.bias"), padding=1))
+    idx = 5
+    for _ in range(cfg.tok_size_mul - 1):                                           # Upsample(x2), Conv1d, ReLU :73-76
+        x = x[:, :, upsample_nearest_index(2 * x.shape[-1], x.shape[-1])]
+        x = F.relu(nm.conv1d(x, g(f"{e}{idx + 1}.weight"), g(f"{e}{idx + 1}.bias"), padding=1))
+        idx += 3
+    x = nm.conv1d(x, g(f"{e}{idx}.0.weight"), g(f"{e}{idx}.0.bias"), padding=1, stride=2)   # Conv1d(W,W,4,2,1) :80-83
+    dils = [cfg.tok_dilation_rate ** d for d in range(cfg.tok_depth)][::-1]
+    for d, dil in enumerate(dils):
+        r = f"{e}{idx}.1.model.{d}."
+        h = nm.conv1d(F.relu(x), g(r + "conv1.weight"), g(r + "conv1.bias"), padding=dil, dilation=dil)
+        h = nm.conv1d(F.relu(h), g(r + "conv2.weight"), g(r + "conv2.bias"), padding=0)
+        x = x + h
+    x = nm.conv1d(x, g(f"{e}{idx + 1}.weight"), g(f"{e}{idx + 1}.bias"), padding=1)          # (B,code_dim,T) :86
+    lat = x.permute(0, 2, 1).contiguous().view(-1, x.shape[1])                      # preprocess, quantize_cnn.py:74-78
+    return vq_quantize(lat, g("quantizer.codebook")), lat
 
 
 def vq_quantize(x: Tensor, codebook: Tensor, chunk: int = 65536) -> Tensor:

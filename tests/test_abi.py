@@ -35,7 +35,7 @@ def test_struct_layouts_match_header_field_counts():
     from tokenhmr_b200 import _lib
     text = (ROOT / "include" / "tokenhmr_b200.h").read_text()
     for cls in (_lib.SmplDesc, _lib.Config, _lib.VitBlock, _lib.DecLayer, _lib.MixerBlock, _lib.Conv, _lib.Weights,
-                _lib.Outputs):
+                _lib.Outputs, _lib.PreprocCfg, _lib.TokConv, _lib.TokEncoderDesc):
         for name, _ in cls._fields_:
             assert re.search(rf"\b{name}\b", text), f"{cls.__name__}.{name} not in header"
     assert ctypes.sizeof(_lib.Outputs) == 12 * ctypes.sizeof(ctypes.c_void_p)

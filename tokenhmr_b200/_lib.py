@@ -71,6 +71,17 @@ class Weights(Structure):
                 ("res_conv1", Conv * 8), ("res_conv2", Conv * 8), ("conv_post", Conv), ("conv_out", Conv)]
 
 
+class TokConv(Structure):
+    _fields_ = [("w", c_void_p), ("b", c_void_p)]
+
+
+class TokEncoderDesc(Structure):
+    _fields_ = [("joints", c_int), ("in_dim", c_int), ("width", c_int), ("depth", c_int), ("dilation_rate", c_int),
+                ("size_mul", c_int), ("code_dim", c_int), ("nb_code", c_int),
+                ("conv_in", TokConv), ("conv_up", TokConv * 8), ("conv_down", TokConv),
+                ("res_conv1", TokConv * 8), ("res_conv2", TokConv * 8), ("conv_out", TokConv), ("codebook", c_void_p)]
+
+
 class PreprocCfg(Structure):
     _fields_ = [("image_size", c_int), ("bbox_w", c_int), ("bbox_h", c_int),
                 ("mean", ctypes.c_double * 3), ("std", ctypes.c_double * 3)]
@@ -125,6 +136,11 @@ SIGNATURES = {
     "thmr_preprocess_plan": (c_int, [c_void_p, c_int, POINTER(PreprocCfg), c_void_p, c_void_p, c_void_p, c_void_p]),
     "thmr_preprocess_boxes": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, POINTER(PreprocCfg), c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "thmr_tok_encoder_create": (c_int, [POINTER(TokEncoderDesc), POINTER(c_void_p)]),
+    "thmr_tok_encoder_destroy": (None, [c_void_p]),
+    "thmr_tok_encoder_num_tokens": (c_int, [c_void_p]),
+    "thmr_tok_encoder_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "thmr_tok_encode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "thmr_smpl_create": (c_int, [POINTER(SmplDesc), POINTER(c_void_p)]),
     "thmr_smpl_destroy": (None, [c_void_p]),
     "thmr_smpl_workspace_bytes": (c_size_t, [c_void_p, c_int]),

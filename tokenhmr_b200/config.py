@@ -48,6 +48,7 @@ class TokenHMRConfig:
     tok_depth: int = 2
     tok_dilation_rate: int = 3
     tok_size_div: int = 4
+    tok_size_mul: int = 4          # ARCH.TOKEN_SIZE_MUL (encoder: 21 -> 40 -> 80 -> 160 -> 320 -> stride 2 -> 160)
     tok_joints: int = 21
     # --- SMPL
     num_verts: int = 6890

@@ -86,6 +86,20 @@ inline int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, u
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, rows, cols, ld, box_rows, box_cols, swz);
 }
 
+// Bump allocator over a caller-provided workspace (1 KB aligned carves; base == nullptr only measures).
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {

@@ -38,19 +38,6 @@ struct Step {
   double bytes;   // algorithmic HBM bytes for bandwidth-bound kernels, 0 otherwise
 };
 
-struct Bump {
-  uint8_t* base;
-  size_t off = 0;
-  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
-  template <typename T>
-  T* take(size_t n) {
-    off = (off + 1023) & ~size_t(1023);
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += n * sizeof(T);
-    return p;
-  }
-};
-
 // ---- SMPL stage (shared by thmr_lbs / thmr_smpl_forward / the engine) -----------------------------------
 // The pose-blend offsets (fp32, 82.7 KB per pose) are produced by a GEMM and consumed by the skinning kernel.
 // Poses are processed in chunks of kSmplChunk so that the offsets of a chunk (42 MB) stay L2-resident between the

@@ -7,6 +7,7 @@
 #include "engine.cuh"
 #include "eval_kernels.cuh"
 #include "preproc.cuh"
+#include "tok_encoder.cuh"
 
 using namespace thmr;
 
@@ -331,6 +332,49 @@ int thmr_preprocess_boxes(const uint8_t* img_bgr, int img_h, int img_w, int64_t 
     THMR_CUDA(cudaGetLastError());
   }
   return THMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tokenizer encoder
+int thmr_tok_encoder_create(const thmr_tok_encoder_desc* d, thmr_tok_encoder** out) {
+  THMR_CHECK(d && out, "tok_encoder_create: null argument");
+  THMR_CHECK(d->joints > 0 && d->in_dim > 0 && d->in_dim <= kEncCin0, "tok_encoder: joints %d in_dim %d (<= %d)", d->joints,
+             d->in_dim, kEncCin0);
+  THMR_CHECK(d->width % 64 == 0 && d->code_dim % 64 == 0 && d->nb_code % 4 == 0, "tok_encoder: width %d code_dim %d nb_code %d",
+             d->width, d->code_dim, d->nb_code);
+  THMR_CHECK(d->depth >= 1 && d->depth <= 8 && d->size_mul >= 1 && d->size_mul <= 8, "tok_encoder: depth %d size_mul %d",
+             d->depth, d->size_mul);
+  THMR_CHECK(d->conv_in.w && d->conv_down.w && d->conv_out.w && d->codebook, "tok_encoder: missing weights");
+  for (int i = 0; i < d->size_mul; ++i) THMR_CHECK(d->conv_up[i].w, "tok_encoder: conv_up[%d] missing", i);
+  for (int i = 0; i < d->depth; ++i)
+    THMR_CHECK(d->res_conv1[i].w && d->res_conv2[i].w, "tok_encoder: resnet block %d missing", i);
+  thmr_tok_encoder* e = new thmr_tok_encoder();
+  e->d = *d;
+  *out = e;
+  return THMR_OK;
+}
+
+void thmr_tok_encoder_destroy(thmr_tok_encoder* e) { delete e; }
+
+int thmr_tok_encoder_num_tokens(const thmr_tok_encoder* e) {
+  if (!e) return 0;
+  int Lmax, T;
+  enc_seq_lens(e->d, &Lmax, &T);
+  return T;
+}
+
+size_t thmr_tok_encoder_workspace_bytes(const thmr_tok_encoder* e, int batch) {
+  if (!e || batch <= 0) return 0;
+  EncWs ws;
+  enc_carve(e->d, nullptr, batch, &ws);
+  return ws.total + 1024;
+}
+
+int thmr_tok_encode(const thmr_tok_encoder* e, const float* pose6d, int B, int64_t* code_idx, float* latent,
+                    void* workspace, void* stream) {
+  THMR_CHECK(e && pose6d && code_idx && workspace, "tok_encode: null argument");
+  THMR_CHECK(B > 0, "tok_encode: bad batch %d", B);
+  void* ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  return enc_run(e, pose6d, B, code_idx, latent, ws, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------ SMPL

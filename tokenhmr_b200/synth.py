@@ -143,6 +143,32 @@ def make_state_dict(cfg: TokenHMRConfig, seed: int = 1234) -> Dict[str, torch.Te
     return m.sd
 
 
+def make_tokenizer_encoder_state_dict(cfg: TokenHMRConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """Synthetic 'tokenizer.encoder.encoder.*' parameters (PoseSPEncoderV1, vanilla_pose_vqvae.py:65-86; Sequential
+    indices as the reference saves them) + 'tokenizer.quantizer.codebook' (the same tensor make_state_dict produces:
+    every tensor is seeded by its own name).  Kept out of make_state_dict: the forward path does not use them."""
+    m = _Maker(seed)
+    W = cfg.tok_width
+    t = "tokenizer.encoder.encoder"
+    m.conv1d(f"{t}.0", W, 6, 3)
+    m.conv1d(f"{t}.3", W, W, 3)
+    idx = 5
+    for _ in range(cfg.tok_size_mul - 1):
+        m.conv1d(f"{t}.{idx + 1}", W, W, 3)
+        idx += 3
+    m.conv1d(f"{t}.{idx}.0", W, W, 4)
+    for d in range(cfg.tok_depth):
+        m.conv1d(f"{t}.{idx}.1.model.{d}.conv1", W, W, 3)
+        m.conv1d(f"{t}.{idx}.1.model.{d}.conv2", W, W, 1)
+    m.conv1d(f"{t}.{idx + 1}", cfg.code_dim, W, 3)
+    # random-init latents are ~0.03 in scale against a unit-variance codebook (every query would pick the code of
+    # smallest norm): scale the last conv so that the arg-min actually depends on the query
+    for n in (f"{t}.{idx + 1}.weight", f"{t}.{idx + 1}.bias"):
+        m.sd[n] = m.sd[n] * 40.0
+    m.normal("tokenizer.quantizer.codebook", (cfg.nb_code, cfg.code_dim), 1.0)
+    return m.sd
+
+
 def make_smpl(cfg: TokenHMRConfig, seed: int = 3) -> Dict[str, torch.Tensor]:
     """Synthetic SMPL-shaped body model (fp32 CPU tensors), keys as the smplx buffers:
     v_template (V,3), shapedirs (V,3,10), posedirs (207, V*3), J_regressor (24,V), lbs_weights (V,24),
