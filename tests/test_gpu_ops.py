@@ -47,6 +47,35 @@ def test_gemm_all_epilogues(cuda_dev, M, N, K, bn):
     assert rel_err(x, ref + resid) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(12288, 1280, 1280), (384, 1280, 1280), (1024, 520, 320), (4608, 1280, 5120), (256, 256, 64)])
+def test_gemm_cta_pair_fp32_epilogues(cuda_dev, M, N, K):
+    """fp32 epilogues (TMA reduce-add, TMA store) of the CTA-pair / CTA-quad kernels at the ViT's proj / fc2 shapes
+    (240 tiles: 3.24 rounds), with fewer tiles than CTA pairs, and with a partial last column tile."""
+    from tokenhmr_b200._lib import check, lib
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=cuda_dev) * 0.5).half()
+    B = (torch.randn(N, K, device=cuda_dev) * 0.5).half()
+    bias = torch.randn(N, device=cuda_dev)
+    resid = torch.randn(M, N, device=cuda_dev)
+    ref = A.float() @ B.float().t() + bias
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        x = resid.clone()      # in-place residual add: TMA reduce-add epilogue
+        check(lib().thmr_gemm_f16(A.data_ptr(), K, B.data_ptr(), K, M, N, K, bias.data_ptr(), x.data_ptr(), N, 0,
+                                  x.data_ptr(), N, None, 0, 512, st))
+        y = torch.full((M, N), float("nan"), device=cuda_dev)   # plain fp32 store epilogue
+        check(lib().thmr_gemm_f16(A.data_ptr(), K, B.data_ptr(), K, M, N, K, bias.data_ptr(), None, 0, 0,
+                                  y.data_ptr(), N, None, 0, 512, st))
+        torch.cuda.synchronize()
+        return x, y
+
+    x, y = run()
+    assert rel_err(x, ref + resid) < 1e-5
+    assert rel_err(y, ref) < 1e-5
+    assert not torch.isnan(y).any()
+
+
 def test_gemm_linearity_at_full_size(cuda_dev):
     """Size-independent property at the ViT's real GEMM shape: f(a1 + a2) == f(a1) + f(a2) up to fp32 noise
     when the fp16 operands are exactly representable sums."""

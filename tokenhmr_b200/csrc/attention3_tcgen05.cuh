@@ -210,13 +210,16 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
     }
   } else if (warp >= 9) {
-    if (lane == 0) {
+    {
       // ---------------------------------------------------------------- MMA issuer of chain g
+      // All 32 lanes walk the chain (uniform control flow: ptxas keeps the descriptors in uniform registers and the 5 / 12
+      // UTCHMMA of a step issue back to back); one elected lane issues.  With a single active lane every descriptor
+      // went through an ELECT / R2UR waterfall loop of ~25 dependent instructions per MMA.
       const int g = warp - 9;
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAttTokens);            // Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc_f16(128, kAttHeadDim, 0, 1);     // P V   : V is N-major
       const uint32_t smem_a = smem_u32(smem);
-      const uint32_t tb = tmem_base + g * kAtt3BufCols;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + g * kAtt3BufCols;
       long long w_oe = 0, w_qk = 0, w_p = 0, w_v = 0;
       const long long t_begin = clock64();
       for (int i = 0; i < nheads; ++i) {
@@ -232,14 +235,17 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait(&qk_full[st], ph);
         w_qk += clock64() - t1;
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kc = 0; kc < kAttChunks; ++kc) {
-          const uint64_t da = make_smem_desc(sQ + kc * kAttChunkBytes + row0 * 32, 16, 256, kSwz32);
-          const uint64_t db = make_smem_desc(sQ + kAttMatBytes + kc * kAttChunkBytes, 16, 256, kSwz32);
-          umma_f16_ss(tb, da, db, idesc_s, kc != 0);
+          for (int kc = 0; kc < kAttChunks; ++kc) {
+            const uint64_t da = make_smem_desc(sQ + kc * kAttChunkBytes + row0 * 32, 16, 256, kSwz32);
+            const uint64_t db = make_smem_desc(sQ + kAttMatBytes + kc * kAttChunkBytes, 16, 256, kSwz32);
+            umma_f16_ss(tb, da, db, idesc_s, kc != 0);
+          }
+          umma_commit(&s_full[g]);
+          umma_commit(&qk_empty[st]);
         }
-        umma_commit(&s_full[g]);
-        umma_commit(&qk_empty[st]);
+        __syncwarp();
         t0 = clock64();
         mbar_wait(&p_full[g], i & 1);
         t1 = clock64();
@@ -250,15 +256,18 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const uint32_t sV = sQ + 2 * kAttMatBytes;
         // (splitting these into two halves that start under the second half of the exponentials is not possible: O
         // aliases S columns 96..175, which pass 2 is still reading, and the 128 spare TMEM columns cannot hold two Os)
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kAttTokens / 16; ++ks) {
-          const uint64_t db = make_smem_desc(sV + ks * 512, kAttChunkBytes, 256, kSwz32);
-          umma_f16_ts(tb + kAtt3ColO, tb + ks * 8, db, idesc_o, ks != 0);
+          for (int ks = 0; ks < kAttTokens / 16; ++ks) {
+            const uint64_t db = make_smem_desc(sV + ks * 512, kAttChunkBytes, 256, kSwz32);
+            umma_f16_ts(tb + kAtt3ColO, tb + ks * 8, db, idesc_o, ks != 0);
+          }
+          umma_commit(&o_full[g]);
+          umma_commit(&v_empty[st]);
         }
-        umma_commit(&o_full[g]);
-        umma_commit(&v_empty[st]);
+        __syncwarp();
       }
-      if (p.dbg_counters) {
+      if (p.dbg_counters && lane == 0) {
         unsigned long long* c = p.dbg_counters + blockIdx.x * 32;
         c[g ? 8 : 0] = clock64() - t_begin;
         c[g ? 15 : 1] = w_oe;

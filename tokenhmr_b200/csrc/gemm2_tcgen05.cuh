@@ -7,7 +7,7 @@
 //
 //   both CTAs : warp 0 TMA producer (own A rows, own half of B; bytes credited to the LEADER's full barrier)
 //               warps 4-11 epilogue of the CTA's own 128 accumulator rows (own TMEM)
-//   leader    : warp 1 issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and multicasts the completion to the
+//   leader    : warp 9 (all lanes walk the pipeline, one elected lane issues) tcgen05.mma.cta_group::2 (M = 256, N = 256) and multicasts the completion to the
 //               "smem slot free" and "accumulator ready" barriers of both CTAs
 //   peer      : its epilogue warps release the accumulator buffer by arriving on the leader's barrier
 //
@@ -94,7 +94,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
           const long long t0 = clock64();
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           w_empty += clock64() - t0;
           uint8_t* sa = smem + stage * kG2StageBytes;
           uint8_t* sb = sa + kG2ABytes;
@@ -110,9 +110,18 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0 && rank == 0) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      // ---------------------------------------------------------- MMA issuer (leader CTA), warp-converged
+      // The whole warp walks the pipeline, so control flow is uniform and ptxas keeps the shared-memory and instruction
+      // descriptors in uniform registers: four UTCHMMA issue back to back.  (With a single active lane every descriptor
+      // went through an ELECT / R2UR waterfall loop, ~85 dependent instructions per k-block: the issuing thread itself
+      // was the critical path -- its counters showed < 3 % of its time waiting for operands or accumulators.)
+      // One elected lane issues the tcgen05 instructions.  The barriers waited on here are signalled by TMA
+      // complete_tx, tcgen05.commit and remote arrives that guard TMEM, never generic-proxy data, so the waits use the
+      // default .cta scope (an .acquire.cluster probe makes ptxas invalidate L1 after every success).
       constexpr uint32_t idesc = make_idesc_f16(2 * kGemmBM, kG2BN);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -125,36 +134,39 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int kb0 = ks * kb_per;
         const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
         long long t0 = clock64();
-        mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         w_tempty += clock64() - t0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kG2BN;
+        const uint32_t d_tmem = tmem_u + acc * kG2BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           if (!ready) {
             t0 = clock64();
-            mbar_wait_cluster(&full_bar[stage], phase);
+            mbar_wait(&full_bar[stage], phase);
             w_full += clock64() - t0;
           }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kG2StageBytes);
+          const uint32_t sa = smem_base + stage * kG2StageBytes;
           const uint32_t sb = sa + kG2ABytes;
           const int nstage = (stage + 1 == kG2Stages) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == kG2Stages) ? (phase ^ 1) : phase;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (k == 1) ready = mbar_try_wait_cluster(&full_bar[nstage], nphase);   // peek the next stage
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
+              const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
+              umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm_mcast(&empty_bar[stage], 3);
+            if (kb == kb1 - 1) umma_commit_2sm_mcast(&tfull_bar[acc], 3);
           }
-          umma_commit_2sm_mcast(&empty_bar[stage], 3);
-          if (kb == kb1 - 1) umma_commit_2sm_mcast(&tfull_bar[acc], 3);
+          __syncwarp();
+          ready = __all_sync(0xffffffffu, mbar_try_wait(&full_bar[nstage], nphase));   // peek the next stage (a hint)
           stage = nstage;
           phase = nphase;
         }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
-      if (p.dbg_counters) {
+      if (p.dbg_counters && lane == 0) {
         p.dbg_counters[blockIdx.x * 16 + 2] = w_tempty;
         p.dbg_counters[blockIdx.x * 16 + 3] = w_full;
         p.dbg_counters[blockIdx.x * 16 + 4] = clock64() - t_begin;
@@ -184,7 +196,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int bc = n0 + half * (kG2BN / 2) + lane * 4;
         if (add_bias && lane * 4 < kG2BN / 2 && bc < p.N) bq = __ldg(reinterpret_cast<const float4*>(p.bias + bc));
       }
-      if (lane == 0) mbar_wait_cluster(&tfull_bar[acc], acc_phase);   // one polling lane per warp
+      if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one polling lane per warp
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1

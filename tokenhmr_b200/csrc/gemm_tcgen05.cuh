@@ -208,25 +208,28 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------ MMA issuer (warp-converged, one elected lane issues)
+      // All 32 lanes walk the pipeline: uniform control flow lets ptxas keep the descriptors in uniform registers and
+      // issue the four UTCHMMA of a k-block back to back (see gemm2_tcgen05.cuh for the measurement behind this).
       constexpr uint32_t idesc = make_idesc_f16(kGemmBM, BN);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
-      // The readiness of the NEXT smem stage is polled between the MMA issues of the current one, so the
-      // latency of mbarrier.try_wait (~100-200 cycles even when the phase is complete) overlaps with tensor work
-      // instead of sitting between two k-blocks.
+      // The readiness of the NEXT smem stage is probed right after the MMA issues of the current one, so the latency of
+      // mbarrier.try_wait (~100-200 cycles even when the phase is complete) overlaps with tensor work.
       bool ready = false;
       for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
         long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         w_tempty += clock64() - t0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_u + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!ready) {
             t0 = clock64();
@@ -234,25 +237,28 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             w_full += clock64() - t0;
           }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
           const uint32_t sb = sa + S::kABytes;
           const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (k == 1) ready = mbar_try_wait(&full_bar[nstage], nphase);   // peek (result is only a hint)
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, kSwz128);
+              const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, kSwz128);
+              umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          ready = __all_sync(0xffffffffu, mbar_try_wait(&full_bar[nstage], nphase));   // peek (result is only a hint)
           stage = nstage;
           phase = nphase;
         }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
-      if (p.dbg_counters) {
+      if (p.dbg_counters && lane == 0) {
         p.dbg_counters[blockIdx.x * 16 + 2] = w_tempty;
         p.dbg_counters[blockIdx.x * 16 + 3] = w_full;
         p.dbg_counters[blockIdx.x * 16 + 4] = clock64() - t_begin;

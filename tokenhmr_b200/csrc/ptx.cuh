@@ -347,6 +347,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t it = 0; it < kSpinLimit; ++it) {
     if (mbar_try_wait_cluster(bar, parity)) return true;
   }
