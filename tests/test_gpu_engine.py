@@ -120,6 +120,26 @@ def test_batch_independence(tiny):
     assert torch.equal(again, full)          # same shape, same kernels: bit-reproducible run to run
 
 
+def test_decoder_full_tile_vs_oracle(tiny):
+    """bs = 64 vs bs = 65 (with THMR_DEC_FUSED=1 the first fills the fused decoder kernel's 64-row tile, dec_fused.cuh,
+    and the second takes the one-launch-per-layer path): the decoder output token of the shared images must agree to
+    accumulation noise, and the bs = 64 result must match the CPU oracle of the decoder (engine contract) on a few rows."""
+    from oracle import tokenhmr_oracle as O
+    from tokenhmr_b200 import synth
+    cfg, sd, smpl, model = tiny
+    img = synth.make_images(65, cfg, seed=21)
+    a = model({"img": img[:64]}, return_taps=True)
+    tok64 = a["_token_out"].clone()
+    b = model({"img": img}, return_taps=True)
+    tok65 = b["_token_out"][:64]
+    assert rel_err(tok64, tok65) < 2e-3
+    rows = [0, 31, 63]
+    with torch.no_grad():
+        ctx = a["_vit_tokens"][rows].cpu()
+        ref = O.decoder_forward(sd, ctx, cfg, O.Numerics(True))
+    assert rel_err(tok64[rows], ref) < 2e-3
+
+
 def test_release_forward_vs_reference_golden(cuda_dev, golden_dir):
     """Full ViT-H/16 depth-32 forward (B=2) against the outputs of the LIVE reference modules (fp32)."""
     from tokenhmr_b200 import synth
