@@ -34,6 +34,18 @@ FLOP_PER_IMAGE = 252.10e9
 PER_GPU_BATCH = 64
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture, scripts/make_profiles.sh -> profiles/r1_traffic.json); None when no capture is committed."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return {"bytes_per_launch": d["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+                "kernel": d["kernel"], "source": str(p.relative_to(ROOT))}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -186,7 +198,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version at INFO/VERSION)
+    os.environ.pop("NCCL_DEBUG", None)     # keep stdout to the single JSON line (any NCCL_DEBUG level prints the version)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
@@ -284,7 +296,7 @@ def main():
         roofline = {"kernel": "gemm_f16_tn_kernel (tcgen05, all ViT/decoder GEMM launches)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
-                    "share_of_step": g_ms / tot_ms, "traffic": None,
+                    "share_of_step": g_ms / tot_ms, "traffic": ncu_traffic(),
                     "whole_step_tflops_per_gpu": B * FLOP_PER_IMAGE / (ms_step * 1e-3) / 1e12}
 
     # ---- (4) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
