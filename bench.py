@@ -250,28 +250,29 @@ def main():
     ms_step = ms_total / args.steps
     value = world * B * 1e3 / ms_step
 
-    # ---- (2) end to end through the public API: pinned host input -> H2D -> forward -> D2H of the results
+    # ---- (2) end to end through the public API: pinned host input -> H2D -> forward -> D2H of the results.
+    # TokenHMRPipeline (the streaming driver a dataloader loop uses, engine.py) double-buffers the device-side
+    # input / output slots: the H2D of batch i+1 overlaps the forward of batch i.  Every step still copies its own
+    # 50 MB input from pinned host memory and reads its own results back; the region is timed from an event in front
+    # of the first H2D (copy stream) to one behind the last D2H (compute stream).
+    from tokenhmr_b200.engine import TokenHMRPipeline
     consumed = ["pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t"]   # demo.py:80-118, pose_utils.py:217-239
-    host_out = {}
+    pipe = TokenHMRPipeline(model, depth=2, read_back=consumed, post=(sharded.all_gather if world > 1 else None))
 
-    def step_e2e():
-        out = model({"img": img_host})
-        if world > 1:
-            out = sharded.all_gather(out)
-        for k in consumed:
-            if k not in host_out:
-                host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
-            host_out[k].copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def run_e2e(n):
+        pending = None
+        for _ in range(n):
+            t = pipe.submit({"img": img_host})
+            if pending is not None:
+                pipe.result(pending)
+            pending = t
+        return pipe.result(pending)
 
-    for _ in range(3):
-        step_e2e()
+    run_e2e(4)                       # builds both slots (plans, graphs, pinned result buffers)
     barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
+    e0.record(pipe._copy)
+    host_out = run_e2e(args.steps)
+    e1.record(pipe._compute)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = world * B * 1e3 / ms_e2e
@@ -317,7 +318,8 @@ def main():
                        "weights": "random-init release architecture (seed 1234)",
                        "l2": "1.4 GB of fp16 weights + 0.6 GB of activations stream through the 126 MB L2 every step (inputs larger than L2, no flush needed)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "read_back": consumed},
+                    "d2h_bytes_per_step": d2h, "read_back": consumed,
+                    "api": "TokenHMRPipeline.submit/result (depth 2: H2D of the next batch overlaps the forward)"},
             "gpu_launches": args.steps * model.num_launches(),
             "launches_per_step": model.num_launches(),
             "clocks": clocks, "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu,

@@ -73,8 +73,8 @@ class TokenHMREngine(nn.Module):
     def num_launches(self) -> int:
         return lib().thmr_engine_num_launches(self._h)
 
-    def _state(self, B: int, taps: bool) -> dict:
-        key = B * 2 + int(taps)
+    def _state(self, B: int, taps: bool, slot: int = 0) -> dict:
+        key = (B, int(taps), slot)
         st = self._bufs.get(key)
         if st is not None:
             return st
@@ -106,14 +106,16 @@ class TokenHMREngine(nn.Module):
                                         torch.cuda.current_stream().cuda_stream))
 
     @torch.no_grad()
-    def forward(self, batch: Dict, return_taps: bool = False) -> Dict:
-        """TokenHMR.forward: only batch['img'] is read (tokenhmr.py:146)."""
+    def forward(self, batch: Dict, return_taps: bool = False, slot: int = 0) -> Dict:
+        """TokenHMR.forward: only batch['img'] is read (tokenhmr.py:146).  `slot` selects an independent set of
+        input / output / workspace buffers (and CUDA graph), so that a caller can have several forwards in flight
+        (TokenHMRPipeline); the returned tensors alias that slot's buffers until its next forward."""
         img = batch["img"]
         if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != self.cfg.image_size or img.shape[3] != self.cfg.image_size:
             raise _lib.ThmrError(f"batch['img'] must be (B,3,{self.cfg.image_size},{self.cfg.image_size}), got {tuple(img.shape)}")
         B = img.shape[0]
         with torch.cuda.device(self.device):
-            st = self._state(B, return_taps)
+            st = self._state(B, return_taps, slot)
             st["t"]["img"].copy_(img.to(torch.float32), non_blocking=True)     # H2D (or D2D) of the batch
             if self.use_cuda_graph:
                 if st["graph"] is None:
@@ -180,6 +182,64 @@ class TokenHMREngine(nn.Module):
             tok = st["t"]["vit_tokens"]
             gh, gw = self.cfg.grid_h, self.cfg.grid_w
             return tok.permute(0, 2, 1).reshape(B, self.cfg.vit_dim, gh, gw).contiguous()
+
+
+class TokenHMRPipeline:
+    """Double-buffered host -> device -> host driver for streams of batches (eval.py / track.py style loops):
+
+        pipe = TokenHMRPipeline(model, read_back=("pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t"))
+        t0 = pipe.submit(batch0)            # H2D of the pinned host batch on the copy stream, forward, D2H: all async
+        t1 = pipe.submit(batch1)            # its H2D overlaps the forward of batch0
+        out0 = pipe.result(t0)              # pinned host tensors (valid until the slot is reused, `depth` submits later)
+
+    Nothing is skipped: every submit copies its own input and every result is read back; only the waiting is moved, so
+    the copy engines work while the SMs run the previous batch.  `post(out)` (optional) runs on the compute stream between
+    the forward and the read-back (e.g. the all-gather of a sharded model)."""
+
+    def __init__(self, model: "TokenHMREngine", depth: int = 2, read_back=("pred_vertices", "pred_keypoints_3d",
+                                                                         "pred_cam", "pred_cam_t"), post=None):
+        self.model, self.depth, self.read_back, self.post = model, int(depth), tuple(read_back), post
+        with torch.cuda.device(model.device):
+            self._copy = torch.cuda.Stream(model.device)
+            self._compute = torch.cuda.Stream(model.device)
+            self._copied = [torch.cuda.Event() for _ in range(self.depth)]
+            self._done = [torch.cuda.Event() for _ in range(self.depth)]
+        self._used = [False] * self.depth
+        self._host = [dict() for _ in range(self.depth)]
+        self._n = 0
+
+    @torch.no_grad()
+    def submit(self, batch: Dict) -> int:
+        ticket = self._n
+        slot = ticket % self.depth
+        self._n += 1
+        m = self.model
+        img = batch["img"]
+        with torch.cuda.device(m.device):
+            st = m._state(img.shape[0], False, slot)
+            with torch.cuda.stream(self._copy):
+                if self._used[slot]:
+                    self._copy.wait_event(self._done[slot])       # the slot's previous forward has consumed its input
+                st["t"]["img"].copy_(img, non_blocking=True)
+                self._copied[slot].record(self._copy)
+            with torch.cuda.stream(self._compute):
+                self._compute.wait_event(self._copied[slot])
+                out = m.forward({"img": st["t"]["img"]}, slot=slot)   # the D2D self-copy of the input is a no-op
+                if self.post is not None:
+                    out = self.post(out)
+                host = self._host[slot]
+                for k in self.read_back:
+                    if k not in host or host[k].shape != out[k].shape:
+                        host[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                    host[k].copy_(out[k], non_blocking=True)
+                self._done[slot].record(self._compute)
+            self._used[slot] = True
+        return ticket
+
+    def result(self, ticket: int) -> Dict[str, torch.Tensor]:
+        slot = ticket % self.depth
+        self._done[slot].synchronize()
+        return self._host[slot]
 
 
 def load_tokenhmr(state_dict: Dict[str, torch.Tensor], smpl: Dict[str, torch.Tensor],
