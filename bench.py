@@ -117,8 +117,10 @@ def pick_cpu_threads(sd, smpl, cfg) -> int:
     return best
 
 
-def cpu_forward_rate(sample_images: int, repeats: int):
-    """The oracle (fp32 CPU restatement of the reference forward) timed on the host cores."""
+def cpu_forward_rate(budget_s: float = 15.0):
+    """The oracle (fp32 CPU restatement of the reference forward) timed on the host cores.  Host speed differs by more
+    than an order of magnitude between boxes, so the sample is sized from a 4-image probe to ~`budget_s` seconds of CPU
+    work (4..64 of the 64 images)."""
     import torch
     from oracle import tokenhmr_oracle as O
     from tokenhmr_b200 import synth
@@ -127,14 +129,17 @@ def cpu_forward_rate(sample_images: int, repeats: int):
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
     threads = pick_cpu_threads(sd, smpl, cfg)
     torch.set_num_threads(threads)
-    img = synth.make_images(sample_images, cfg)
-    times = []
     with torch.no_grad():
-        for _ in range(repeats):
-            t = time.perf_counter()
-            O.forward(sd, smpl, img, cfg)
-            times.append(time.perf_counter() - t)
-    return sample_images / min(times), times, threads
+        probe = synth.make_images(4, cfg)
+        t = time.perf_counter()
+        O.forward(sd, smpl, probe, cfg)
+        t4 = time.perf_counter() - t
+        n = max(4, min(64, int(budget_s / t4 * 4) // 4 * 4))
+        img = synth.make_images(n, cfg)
+        t = time.perf_counter()
+        O.forward(sd, smpl, img, cfg)
+        dt = time.perf_counter() - t
+    return n / dt, n, dt, threads
 
 
 def run_reference(args):
@@ -145,7 +150,6 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    sample = 4                                   # images per step: a bounded sample of the bs=64 workload
     from oracle import tokenhmr_oracle as O
     from tokenhmr_b200 import synth
     from tokenhmr_b200.config import release_config
@@ -153,6 +157,14 @@ def run_reference(args):
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
     threads = pick_cpu_threads(sd, smpl, cfg)
     torch.set_num_threads(threads)
+    # images per step: a bounded sample of the bs=64 workload, sized from a 4-image probe so that one step is ~10 s of
+    # CPU work on this host (4..64 images)
+    with torch.no_grad():
+        probe = synth.make_images(4, cfg)
+        t = time.perf_counter()
+        O.forward(sd, smpl, probe, cfg)
+        t4 = time.perf_counter() - t
+    sample = max(4, min(64, int(10.0 / t4 * 4) // 4 * 4))
     img = synth.make_images(sample, cfg)
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -303,10 +315,10 @@ def main():
     # ---- (4) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, times, threads = cpu_forward_rate(sample_images=4, repeats=2)
+        v, n, dt, threads = cpu_forward_rate()
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"4 of the 64 images, best of 2 fp32 eager-torch forwards of the oracle ({min(times):.1f}s), "
-                         f"thread count picked from 8/16/32/64/{os.cpu_count()}"}
+               "sample": f"{n} of the 64 images, one fp32 eager-torch forward of the oracle ({dt:.1f} s, sized from a "
+                         f"4-image probe), thread count picked from 8/16/32/64/{os.cpu_count()}"}
 
     if rank == 0:
         print(json.dumps({
