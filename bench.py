@@ -282,9 +282,9 @@ def main():
 
     run_e2e(4)                       # builds both slots (plans, graphs, pinned result buffers)
     barrier()
-    e0.record(pipe._copy)
+    e0.record(pipe.copy_stream)
     host_out = run_e2e(args.steps)
-    e1.record(pipe._compute)
+    e1.record(pipe.compute_stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = world * B * 1e3 / ms_e2e

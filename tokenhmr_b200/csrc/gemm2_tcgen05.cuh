@@ -180,6 +180,11 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     constexpr int kChunkCols = (EPI == kEpiStore16) ? 64 : 32;
     constexpr int kChunksPerHalf = kG2BN / kChunkCols / 2;
     uint8_t* stage_buf = smem + kG2StagingOffset + warp * 4096;
+    // Slab stores: the four row-quarter warps of a column half stage their 32 rows side by side (their 4 KB buffers are
+    // contiguous and share the 128B-swizzle phase), meet at a named barrier and ONE thread issues a 128-row TMA store:
+    // 4 (fp16) / 8 (fp32) TMA operations per tile and CTA instead of 16 / 32.  THMR_GEMM_DBG bit 7 = per-warp stores.
+    const bool slab = !(p.dbg & 128);
+    uint8_t* slab_buf = smem + kG2StagingOffset + half * 4 * 4096;
     const uint32_t srow = smem_u32(stage_buf) + lane * 128;
     const int sw = lane & 7;
     int acc = 0;
@@ -251,8 +256,13 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             pk[j + 3] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[j + 3]), b4.w));
           }
         }
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
+        if (slab) {
+          if (q == 0 && lane == 0) tma_store_wait_read<0>();     // the previous slab has been read out of smem
+          named_bar_sync_128(1 + half);
+        } else {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ sw) << 4)), "r"(pk[4 * j]),
@@ -260,12 +270,22 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                        : "memory");
         }
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
-          if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
-          else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
-          else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
-          tma_store_commit();
+        if (slab) {
+          named_bar_sync_128(1 + half);
+          if (q == 0 && lane == 0 && col0 < p.N && m0 < p.M && !(p.dbg & 2)) {
+            if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, slab_buf, col0, m0);
+            else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, slab_buf, col0, m0);
+            else tma_reduce_add_2d(&tmC, slab_buf, col0, m0);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
+            if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);
+            tma_store_commit();
+          }
         }
       }
       tc_fence_before();

@@ -149,11 +149,13 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, b_box_rows, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   plan->bn = two ? kG2BN : bn;
   plan->epi = epi;
+  // output boxes: 32 rows per epilogue warp, or (CTA-pair kernel, default) one 128-row slab per column half
+  const uint32_t c_rows = (two && !quad && !(p.dbg & 128)) ? 128 : 32;
   if (epi == kEpiStore16)
-    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, 32, 64,
+    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, c_rows, 64,
                           CU_TENSOR_MAP_SWIZZLE_128B));
   else if (epi == kEpiAdd32 || epi == kEpiStore32)
-    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out32, d.M, d.N, d.ld32, 32, 32,
+    THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out32, d.M, d.N, d.ld32, c_rows, 32,
                           CU_TENSOR_MAP_SWIZZLE_128B));
   else
     plan->tmC = plan->tmA;

@@ -120,6 +120,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ void named_bar_sync_64(int id) {
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync_128(int id) {
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
                :

@@ -200,8 +200,8 @@ class TokenHMRPipeline:
                                                                          "pred_cam", "pred_cam_t"), post=None):
         self.model, self.depth, self.read_back, self.post = model, int(depth), tuple(read_back), post
         with torch.cuda.device(model.device):
-            self._copy = torch.cuda.Stream(model.device)
-            self._compute = torch.cuda.Stream(model.device)
+            self.copy_stream = torch.cuda.Stream(model.device)
+            self.compute_stream = torch.cuda.Stream(model.device)
             self._copied = [torch.cuda.Event() for _ in range(self.depth)]
             self._done = [torch.cuda.Event() for _ in range(self.depth)]
         self._used = [False] * self.depth
@@ -217,13 +217,13 @@ class TokenHMRPipeline:
         img = batch["img"]
         with torch.cuda.device(m.device):
             st = m._state(img.shape[0], False, slot)
-            with torch.cuda.stream(self._copy):
+            with torch.cuda.stream(self.copy_stream):
                 if self._used[slot]:
-                    self._copy.wait_event(self._done[slot])       # the slot's previous forward has consumed its input
+                    self.copy_stream.wait_event(self._done[slot])       # the slot's previous forward has consumed its input
                 st["t"]["img"].copy_(img, non_blocking=True)
-                self._copied[slot].record(self._copy)
-            with torch.cuda.stream(self._compute):
-                self._compute.wait_event(self._copied[slot])
+                self._copied[slot].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self._copied[slot])
                 out = m.forward({"img": st["t"]["img"]}, slot=slot)   # the D2D self-copy of the input is a no-op
                 if self.post is not None:
                     out = self.post(out)
@@ -232,7 +232,7 @@ class TokenHMRPipeline:
                     if k not in host or host[k].shape != out[k].shape:
                         host[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
                     host[k].copy_(out[k], non_blocking=True)
-                self._done[slot].record(self._compute)
+                self._done[slot].record(self.compute_stream)
             self._used[slot] = True
         return ticket
 
