@@ -193,6 +193,23 @@ def encoder_goldens(ns) -> None:
     print("wrote tok_encoder golden:", idx_a.unique().numel(), "/", idx_b.unique().numel(), "distinct codes")
 
 
+def rodrigues_goldens(ns) -> None:
+    """Axis-angle -> rotation matrix by the reference's OWN two implementations (geometry.aa_to_rotmat, via a quaternion,
+    geometry.py:5-46; rotation_utils.axis_angle_to_matrix, rotation_utils.py:411-443).  smplx's batch_rodrigues is not in
+    the tree (parity of the SMPL stage stays unpinned), but its first step must agree with these: a cross-check of
+    oracle/smpl_oracle.batch_rodrigues and of thmr_lbs(pose2rot=1) that does come from reference code."""
+    import importlib
+    rot = importlib.import_module("lib.utils.rotation_utils")
+    g = torch.Generator().manual_seed(17)
+    aa = torch.cat([1.2 * torch.randn(120, 3, generator=g), 1e-4 * torch.randn(8, 3, generator=g)])
+    with torch.no_grad():
+        R_quat = ns.geometry.aa_to_rotmat(aa)
+        R_p3d = rot.axis_angle_to_matrix(aa)
+    np.savez_compressed(GOLDEN / "rodrigues_ref.npz", aa=aa.numpy(), R_aa_to_rotmat=R_quat.numpy(),
+                        R_axis_angle_to_matrix=R_p3d.numpy())
+    print("wrote rodrigues golden")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--release", action="store_true")
@@ -206,6 +223,9 @@ def main() -> None:
     if args.only == "preproc":
         preproc_goldens()
         return
+    if args.only == "rodrigues":
+        rodrigues_goldens(ref_import.load_modules())
+        return
     if args.only == "encoder":
         encoder_goldens(ref_import.load_modules())
         return
@@ -214,6 +234,7 @@ def main() -> None:
     eval_goldens()
     preproc_goldens()
     encoder_goldens(ns)
+    rodrigues_goldens(ns)
     forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
     if args.release:
         forward_golden(ns, release_config(), 2, "forward_release_d32.npz")

@@ -7,6 +7,9 @@ smplx/body_models.py (SMPLLayer.forward) and smplx/vertex_joint_selector.py, and
 reference's own call sites:
     tokenhmr/lib/models/smpl_wrapper.py:10,19-24,27-41   (SMPL(smplx.SMPLLayer), joint_map, extra regressor)
     tokenhmr/lib/models/tokenhmr.py:173-176              (self.smpl(..., pose2rot=False))
+The one piece the reference tree can vouch for is cross-checked against it: batch_rodrigues agrees to 2e-6 with the
+reference's own axis-angle converters (geometry.aa_to_rotmat, rotation_utils.axis_angle_to_matrix) through
+tests/golden/rodrigues_ref.npz (oracle/make_golden.py --only rodrigues).
 Known-answer checks lifted from the algorithm itself (tests/test_oracle_smpl.py): identity pose gives
 v_template + shapedirs.beta; a global rotation rotates the rest mesh about the root joint; batch_rodrigues
 of a zero vector is I; 90-degree rotations about the axes give the textbook matrices.

@@ -76,3 +76,12 @@ def test_f64_fixture_is_reproduced(golden_dir):
     v, j = S.smpl_forward(m, R[:, :1], R[:, 1:], betas)
     torch.testing.assert_close(v, torch.from_numpy(g["verts"]), atol=2e-6, rtol=0)
     torch.testing.assert_close(j, torch.from_numpy(g["joints"]), atol=2e-6, rtol=0)
+
+
+def test_rodrigues_agrees_with_the_references_own_converters(golden_dir):
+    """smplx is absent, but the reference carries two axis-angle -> matrix routines of its own (geometry.aa_to_rotmat,
+    rotation_utils.axis_angle_to_matrix): the restated batch_rodrigues must agree with what they produced."""
+    g = np.load(golden_dir / "rodrigues_ref.npz")
+    R = S.batch_rodrigues(torch.from_numpy(g["aa"]))
+    np.testing.assert_allclose(R.numpy(), g["R_aa_to_rotmat"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(R.numpy(), g["R_axis_angle_to_matrix"], rtol=0, atol=2e-6)
