@@ -162,6 +162,7 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const int nheads = (p.num_problems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                      static_cast<int>(gridDim.x);
 
+  pdl_launch_dependents();
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmO);
@@ -186,6 +187,7 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // Q, K, V are the predecessor's output
 
   if (warp == 8) {
     // ---------------------------------------------------------------- TMA producers: lane 0 streams Q,K, lane 1 streams V
@@ -398,8 +400,8 @@ inline int attention3_launch_t(const AttnPlan& plan, cudaStream_t st) {
                                    kAtt3SmemBytes));
     configured = true;
   }
-  vit_attention3_kernel<POLY, DBG><<<plan.grid, kAtt3Threads, kAtt3SmemBytes, st>>>(plan.tm, plan.tm_out, plan.p);
-  THMR_CUDA(cudaGetLastError());
+  THMR_CUDA(launch_pdl(vit_attention3_kernel<POLY, DBG>, plan.grid, kAtt3Threads, kAtt3SmemBytes, st, plan.tm, plan.tm_out,
+                       plan.p));
   return THMR_OK;
 }
 

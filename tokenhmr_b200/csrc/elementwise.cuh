@@ -64,11 +64,13 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   extern __shared__ float4 s_gb[];   // [2][C/4]
   float4* sg = s_gb;
   float4* sb = s_gb + C / 4;
+  pdl_launch_dependents();
   for (int c = threadIdx.x; c < C / 4; c += blockDim.x) {
     sg[c] = reinterpret_cast<const float4*>(gamma)[c];
     sb[c] = reinterpret_cast<const float4*>(beta)[c];
   }
   __syncthreads();
+  pdl_wait();       // gamma / beta are weights; x is the predecessor's output
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   auto load_row = [&](float4 (&v)[VEC4], int row) {
@@ -192,10 +194,10 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
     const int vec4 = (C / 4 + 31) / 32;
 #define THMR_LN_LAUNCH(V)                                                                                           \
   do {                                                                                                             \
-    if (prefetch) layernorm_reg_kernel<V, true><<<grid, threads, smem, st>>>(x, gamma, beta, y16, ld16, y32, R, C, \
-                                                                            eps, relu, out_t);                    \
-    else layernorm_reg_kernel<V, false><<<grid, threads, smem, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps,    \
-                                                                     relu, out_t);                                \
+    if (prefetch) THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, true>, grid, threads, smem, st, x, gamma, beta, y16, \
+                                       ld16, y32, R, C, eps, relu, out_t));                                        \
+    else THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, false>, grid, threads, smem, st, x, gamma, beta, y16, ld16,   \
+                              y32, R, C, eps, relu, out_t));                                                       \
   } while (0)
     if (vec4 <= 1) THMR_LN_LAUNCH(1);
     else if (vec4 <= 8) THMR_LN_LAUNCH(8);

@@ -52,6 +52,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int kb_per = (num_kb + ksplit - 1) / ksplit;
   const int num_tiles = tiles_m * tiles_n * ksplit;
 
+  pdl_launch_dependents();
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -77,6 +78,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   cluster_sync_all();     // peer barriers initialised, both TMEM allocations done
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // barriers, TMEM and descriptors are set up; operands / outputs belong to the predecessor until here
 
   if (warp == kWarpTma) {
     if (lane == 0) {

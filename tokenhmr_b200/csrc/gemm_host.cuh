@@ -215,9 +215,8 @@ inline int gemm2_launch_t(const GemmPlan& plan, cudaStream_t stream) {
                                    kG2SmemTotal));
     configured = true;
   }
-  gemm_f16_tn_2cta_kernel<EPI><<<plan.grid, kGemmThreads, kG2SmemTotal, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p,
-                                                                                  plan.ksplit);
-  THMR_CUDA(cudaGetLastError());
+  THMR_CUDA(launch_pdl(gemm_f16_tn_2cta_kernel<EPI>, plan.grid, kGemmThreads, kG2SmemTotal, stream, plan.tmA, plan.tmB,
+                       plan.tmC, plan.p, plan.ksplit));
   return THMR_OK;
 }
 
