@@ -63,7 +63,6 @@ class _StubDict(dict):
     def __setstate__(self, state):
         if isinstance(state, dict):
             self.update(state)
-            self.__dict__.update({})
 
 
 def _stub_class(module: str, name: str):
