@@ -41,6 +41,30 @@ def test_struct_layouts_match_header_field_counts():
     assert ctypes.sizeof(_lib.Outputs) == 12 * ctypes.sizeof(ctypes.c_void_p)
 
 
+def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
+    """include/tokenhmr_b200.h must compile as C (the boundary is a C ABI) and every struct mirrored in _lib.py must
+    have the size the C compiler gives it."""
+    import shutil
+    import subprocess
+    from tokenhmr_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = [("thmr_smpl_desc", _lib.SmplDesc), ("thmr_config", _lib.Config), ("thmr_vit_block", _lib.VitBlock),
+             ("thmr_dec_layer", _lib.DecLayer), ("thmr_mixer_block", _lib.MixerBlock), ("thmr_conv", _lib.Conv),
+             ("thmr_weights", _lib.Weights), ("thmr_outputs", _lib.Outputs), ("thmr_preproc_cfg", _lib.PreprocCfg),
+             ("thmr_tok_conv", _lib.TokConv), ("thmr_tok_encoder_desc", _lib.TokEncoderDesc)]
+    src = tmp_path / "sizes.c"
+    body = "".join(f'  printf("%s %zu\\n", "{n}", sizeof({n}));\n' for n, _ in pairs)
+    src.write_text(f'#include <stdio.h>\n#include "{ROOT / "include" / "tokenhmr_b200.h"}"\nint main(void) {{\n{body}  return 0;\n}}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = dict(zip(out[0::2], map(int, out[1::2])))
+    for name, cls in pairs:
+        assert sizes[name] == ctypes.sizeof(cls), f"{name}: C {sizes[name]} vs ctypes {ctypes.sizeof(cls)}"
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from tokenhmr_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
