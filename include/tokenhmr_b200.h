@@ -225,6 +225,10 @@ typedef struct thmr_config {
   int n_upsample;                                     /* 4 */
   int upsample_sizes[8];                              /* 125, 90, 55, 21 */
   float focal_length;                                 /* 5000 */
+  int strict;   /* 0: fp16 operands / fp32 accumulate (default).  1: every contraction in split fp16 (3 tensor-core
+                 * products, ~2^-21 relative = fp32-grade, the reference's arithmetic: demo.py:35-37 runs fp32); all
+                 * "w" matrices of thmr_weights are then f16 [out, 3*in] = [hi | hi | lo] of w * 2^8 (per tap for convs),
+                 * as packed by tokenhmr_b200/weights.py with strict=True. */
 } thmr_config;
 
 /* Weight pointers, packed by the host loader (tokenhmr_b200/weights.py) from the reference state_dicts.
@@ -320,6 +324,29 @@ int thmr_engine_profile(thmr_engine* e, const float* img, int B, const thmr_outp
                         void* stream, float* step_ms, int cap);
 /* Backbone only: ViT.forward [vit.py:341-343]: img -> tokens fp32 [B,192,D] (token-major). */
 int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange.  The path shards by image with no data-path collective;
+ * the one exchange is an all-gather of the per-image outputs (BASELINE.json configs[2]: "NCCL all-gather of
+ * SMPL params/vertices").  In-place design: each output field is ONE device buffer of nranks * rows_per_rank
+ * images on every rank; rank r runs thmr_engine_forward with its thmr_outputs pointing at rows
+ * [r * rows_per_rank, (r+1) * rows_per_rank) of those buffers, then thmr_allgather_outputs() fills in the other
+ * ranks' rows with one grouped ncclAllGather (sendbuff = recvbuff + rank * count), stream-ordered and
+ * CUDA-graph capturable together with the forward.  Replaces the reference's single-process
+ * `model(batch)` over the whole batch (tokenhmr/eval.py:146-147) when the batch is split over GPUs.
+ * NCCL is loaded at run time (libnccl.so.2; override with THMR_NCCL_LIB). */
+typedef struct thmr_comm thmr_comm;
+/* 128-byte NCCL unique id, created on one rank and distributed to the others by the caller (any transport). */
+int thmr_comm_unique_id(void* id128);
+/* Collective over all ranks; uses the calling thread's current CUDA device. */
+int thmr_comm_create(const void* id128, int nranks, int rank, thmr_comm** out);
+void thmr_comm_destroy(thmr_comm* c);
+int thmr_comm_nranks(const thmr_comm* c);
+int thmr_comm_rank(const thmr_comm* c);
+/* `global`: base pointers of the nranks * rows_per_rank buffers (NULL fields are skipped; the taps are never
+ * gathered; cls_logits_softmax is gathered only when its pointer is non-NULL: 1.3 MB per image). */
+int thmr_allgather_outputs(const thmr_engine* e, thmr_comm* c, const thmr_outputs* global, int rows_per_rank,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,20 +24,36 @@ GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
 W_SEED, SMPL_SEED, IMG_SEED = 1234, 3, 0
 
 
-def forward_golden(ns, cfg, batch: int, name: str) -> None:
+def forward_golden(ns, cfg, batch: int, name: str, img_seed: int = IMG_SEED, vert_stride: int = 1) -> None:
+    """vert_stride > 1 (the bs=64 golden): vertices every `vert_stride`-th, no token / probability sub-samples."""
     sd = synth.make_state_dict(cfg, W_SEED)
     smpl = synth.make_smpl(cfg, SMPL_SEED)
-    img = synth.make_images(batch, cfg, IMG_SEED)
+    img = synth.make_images(batch, cfg, img_seed)
     bb = ref_import.build_backbone(ns, sd, cfg)
     head = ref_import.build_head(ns, sd, cfg)
     out = ref_import.reference_forward(ns, bb, head, smpl, img, cfg)
     probs = out["cls_logits_softmax"]
+    top2 = probs.topk(2, dim=-1).values
+    if vert_stride > 1:
+        np.savez_compressed(
+            GOLDEN / name,
+            meta=np.array([W_SEED, SMPL_SEED, img_seed, batch, cfg.vit_depth, cfg.num_verts, vert_stride]),
+            cls_argmax=probs.argmax(-1).numpy().astype(np.int16),
+            cls_maxprob=top2[..., 0].numpy(), cls_second_prob=top2[..., 1].numpy(),
+            pred_cam=out["pred_cam"].numpy(), pred_cam_t=out["pred_cam_t"].numpy(),
+            betas=out["pred_smpl_params"]["betas"].numpy(),
+            global_orient=out["pred_smpl_params"]["global_orient"].numpy(),
+            pred_keypoints_3d=out["pred_keypoints_3d"].numpy(),
+            pred_vertices_sub=out["pred_vertices"][:, ::vert_stride].numpy(),
+            pred_keypoints_2d=out["pred_keypoints_2d"].numpy())
+        print("wrote", name)
+        return
     np.savez_compressed(
         GOLDEN / name,
-        meta=np.array([W_SEED, SMPL_SEED, IMG_SEED, batch, cfg.vit_depth, cfg.num_verts]),
+        meta=np.array([W_SEED, SMPL_SEED, img_seed, batch, cfg.vit_depth, cfg.num_verts]),
         vit_tokens_sub=out["_vit_tokens"][:, ::8].numpy(),          # every 8th token, all channels
         cls_argmax=probs.argmax(-1).numpy().astype(np.int16),
-        cls_maxprob=probs.max(-1).values.numpy(),
+        cls_maxprob=top2[..., 0].numpy(), cls_second_prob=top2[..., 1].numpy(),
         cls_probs_sub=probs[:, ::16].numpy().astype(np.float32),     # every 16th token position, all classes
         pred_cam=out["pred_cam"].numpy(), pred_cam_t=out["pred_cam_t"].numpy(),
         focal_length=out["focal_length"].numpy(),
@@ -229,6 +245,13 @@ def main() -> None:
     if args.only == "encoder":
         encoder_goldens(ref_import.load_modules())
         return
+    if args.only == "forward":
+        ns = ref_import.load_modules()
+        forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
+        if args.release:
+            forward_golden(ns, release_config(), 2, "forward_release_d32.npz")
+            forward_golden(ns, release_config(), 64, "forward_release_d32_bs64.npz", img_seed=5, vert_stride=16)
+        return
     ns = ref_import.load_modules()
     stage_goldens(ns)
     eval_goldens()
@@ -238,6 +261,7 @@ def main() -> None:
     forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
     if args.release:
         forward_golden(ns, release_config(), 2, "forward_release_d32.npz")
+        forward_golden(ns, release_config(), 64, "forward_release_d32_bs64.npz", img_seed=5, vert_stride=16)
 
 
 if __name__ == "__main__":

@@ -138,7 +138,7 @@ def test_lightning_and_tokenizer_checkpoints(tmp_path):
     assert "tokenizer.encoder.encoder.0.weight" in merged
 
     (tmp_path / "model_config.yaml").write_text(
-        "MODEL:\n  IMAGE_SIZE: 256\n  BBOX_SHAPE: [192, 256]\n  SMPL_HEAD:\n    TOKENIZER: {TOKEN_CODE_DIM: 256, TOKEN_NUM: 160, "
+        "MODEL:\n  IMAGE_SIZE: 256\n  BBOX_SHAPE: [192, 256]\n  SMPL_HEAD:\n    TYPE: token\n    TOKENIZER: {TOKEN_CODE_DIM: 256, TOKEN_NUM: 160, "
         "TOKEN_CLASS_NUM: 2048}\n    TRANSFORMER_DECODER: {depth: 6, heads: 8, mlp_dim: 1024, dim_head: 64}\nEXTRA:\n  FOCAL_LENGTH: 5000\n")
     c2 = C.config_from_files(str(tmp_path / "model_config.yaml"), arch2)
     from tokenhmr_b200.config import release_config
@@ -173,3 +173,111 @@ def test_load_tokenhmr_from_files_runs(tmp_path, cuda_dev):
     out = model({"img": img})
     for k in ("pred_vertices", "pred_keypoints_3d", "pred_cam", "cls_logits_softmax"):
         assert torch.equal(out[k], ref[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Variants of the reference the engine does not implement must be rejected, not silently run as the release path
+_BASE_YAML = {
+    "MODEL": {"IMAGE_SIZE": 256, "BBOX_SHAPE": [192, 256], "BACKBONE": {"TYPE": "vit"},
+              "SMPL_HEAD": {"TYPE": "token", "TOKENIZER": {"TOKEN_CODE_DIM": 256, "TOKEN_NUM": 160, "TOKEN_CLASS_NUM": 2048,
+                                                          "TOKENIZER_TYPE": "Vanilla"},
+                            "TRANSFORMER_DECODER": {"depth": 6, "heads": 8, "mlp_dim": 1024, "dim_head": 64, "norm": "layer",
+                                                    "context_dim": 1280}}},
+    "SMPL": {"NUM_BODY_JOINTS": 23, "GENDER": "neutral"}, "EXTRA": {"FOCAL_LENGTH": 5000},
+}
+
+
+def _yaml_with(tmp_path, path, value):
+    import copy
+    import yaml
+    y = copy.deepcopy(_BASE_YAML)
+    node = y
+    for k in path[:-1]:
+        node = node.setdefault(k, {})
+    node[path[-1]] = value
+    p = tmp_path / ("cfg_" + "_".join(path) + ".yaml")
+    p.write_text(yaml.safe_dump(y))
+    return str(p)
+
+
+def test_release_yaml_is_accepted(tmp_path):
+    import yaml
+    from tokenhmr_b200.config import release_config
+    p = tmp_path / "ok.yaml"
+    p.write_text(yaml.safe_dump(_BASE_YAML))
+    assert C.config_from_files(str(p), {"NB_CODE": 2048, "CODE_DIM": 256}) == release_config()
+
+
+@pytest.mark.parametrize("path,value", [
+    (("MODEL", "SMPL_HEAD", "TYPE"), "transformer_decoder"),        # heads/__init__.py:4-13
+    (("MODEL", "SMPL_HEAD", "IEF_ITERS"), 3),                       # token_head.py:86
+    (("MODEL", "SMPL_HEAD", "TRANSFORMER_INPUT"), "mean_shape"),    # token_head.py:29,88-91
+    (("MODEL", "SMPL_HEAD", "JOINT_REP"), "aa"),                    # token_head.py:23-24
+    (("MODEL", "SMPL_HEAD", "TOKENIZER", "TOKENIZER_TYPE"), "parts"),
+    (("MODEL", "SMPL_HEAD", "TRANSFORMER_DECODER", "norm"), "batch"),
+    (("MODEL", "SMPL_HEAD", "TRANSFORMER_DECODER", "dim_head"), 32),
+    (("MODEL", "BACKBONE", "TYPE"), "resnet"),
+    (("SMPL", "update_hips"), True),                                 # smpl_wrapper.py:33-36
+    (("SMPL", "NUM_BODY_JOINTS"), 21),
+])
+def test_unsupported_reference_variants_are_rejected(tmp_path, path, value):
+    from tokenhmr_b200._lib import ThmrError
+    with pytest.raises(ThmrError, match="unsupported configuration"):
+        C.config_from_files(_yaml_with(tmp_path, path, value), None)
+
+
+def test_weights_that_contradict_the_config_are_rejected():
+    import dataclasses
+    from tokenhmr_b200._lib import ThmrError
+    cfg = tiny_config()
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    C.validate_against_weights(cfg, sd, smpl)                                      # consistent: passes
+    with pytest.raises(ThmrError, match="NB_CODE"):
+        C.validate_against_weights(dataclasses.replace(cfg, nb_code=1024), sd, smpl)
+    bad = dict(sd)
+    bad["tokenizer.quantizer.codebook"] = torch.zeros(1024, cfg.code_dim)
+    with pytest.raises(ThmrError, match="codebook"):
+        C.validate_against_weights(cfg, bad, smpl)
+    bad = dict(sd)
+    bad["smpl_head.transformer.to_token_embedding.weight"] = torch.zeros(1024, 157)    # 'mean_shape' checkpoint
+    with pytest.raises(ThmrError, match="mean_shape"):
+        C.validate_against_weights(cfg, bad, smpl)
+    no_extra = {k: v for k, v in smpl.items() if k != "joint_regressor_extra"}
+    with pytest.warns(UserWarning, match="25 instead of 44"):
+        C.validate_against_weights(cfg, sd, no_extra)
+
+
+@pytest.mark.gpu
+def test_engine_device_moves_outputs_and_batch_limit(cuda_dev):
+    """`.to()` of another device raises (it used to be a silent no-op), forward returns fresh tensors by default (the
+    reference's behaviour), and max_batch is enforced."""
+    from tokenhmr_b200._lib import ThmrError
+    from tokenhmr_b200.engine import TokenHMREngine
+    cfg = tiny_config(vit_depth=1)
+    model = TokenHMREngine(cfg, synth.make_state_dict(cfg), synth.make_smpl(cfg), device=cuda_dev, use_cuda_graph=False,
+                           max_batch=4, max_cached_shapes=2)
+    assert model.to(cuda_dev) is model and model.to("cuda:0") is model and model.eval() is model
+    assert model.to(torch.float32) is model
+    for bad in ("cpu", torch.device("cpu"), torch.float16):
+        with pytest.raises(ThmrError):
+            model.to(bad)
+    with pytest.raises(ThmrError):
+        model.cpu()
+    with pytest.raises(ThmrError):
+        model.half()
+    a = model({"img": synth.make_images(2, cfg, seed=1)})
+    keep = a["pred_vertices"]
+    snapshot = keep.clone()
+    b = model({"img": synth.make_images(2, cfg, seed=2)})
+    assert torch.equal(keep, snapshot) and not torch.equal(b["pred_vertices"], keep)       # no aliasing by default
+    c1 = model({"img": synth.make_images(2, cfg, seed=1)}, alias_outputs=True)["pred_vertices"]
+    assert torch.equal(c1, snapshot)
+    model({"img": synth.make_images(2, cfg, seed=2)}, alias_outputs=True)
+    assert not torch.equal(c1, snapshot)                                                    # opt-in views do alias
+    with pytest.raises(ThmrError, match="max_batch"):
+        model({"img": synth.make_images(5, cfg)})
+    for B in (1, 2, 3, 4, 1):                                # more shapes than max_cached_shapes: LRU eviction, still correct
+        out = model({"img": synth.make_images(B, cfg, seed=1)})
+        assert out["pred_vertices"].shape[0] == B
+    assert len(model._bufs) <= 2
+    assert torch.equal(model({"img": synth.make_images(2, cfg, seed=1)})["pred_vertices"], snapshot)

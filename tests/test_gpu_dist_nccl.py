@@ -1,0 +1,73 @@
+"""World-size-2 test of the NATIVE exchange (C ABI thmr_comm_* / thmr_allgather_outputs: in-place grouped
+ncclAllGather inside the forward's CUDA graph) on two real GPUs.  Skipped on boxes with a single GPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q, global_batch, use_graph):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        # the process group only carries the 128-byte NCCL unique id and the shard sizes: gloo is enough, the data
+        # path is the library's own communicator
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from tokenhmr_b200 import synth
+        from tokenhmr_b200.config import tiny_config
+        from tokenhmr_b200.dist import ShardedTokenHMR, shard_range
+        from tokenhmr_b200.engine import TokenHMREngine
+        cfg = tiny_config(vit_depth=1)
+        sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+        model = TokenHMREngine(cfg, sd, smpl, device=f"cuda:{rank}", use_cuda_graph=use_graph)
+        sharded = ShardedTokenHMR(model)
+        assert sharded.transport == "native"
+        img = synth.make_images(global_batch, cfg, seed=11)
+        lo, hi = shard_range(global_batch, rank, world)
+        errs = {}
+        for it in range(3):                       # eager warm-up, capture, replay
+            got = sharded({"img": img[lo:hi]})
+        torch.cuda.synchronize()
+        want = model({"img": img})                # the whole batch on this GPU alone
+        flat = lambda o: {**{k: v for k, v in o.items() if isinstance(v, torch.Tensor)}, **o["pred_smpl_params"]}
+        g, w = flat(got), flat(want)
+        for k in ("pred_vertices", "pred_keypoints_3d", "pred_keypoints_2d", "pred_cam", "pred_cam_t", "focal_length",
+                  "global_orient", "body_pose", "betas"):
+            assert g[k].shape == w[k].shape, (k, g[k].shape, w[k].shape)
+            errs[k] = ((g[k] - w[k]).abs().max() / (w[k].abs().max() + 1e-12)).item()
+        # this rank's own rows are bit-identical to what its local forward wrote (in-place: nothing was copied)
+        local = model({"img": img[lo:hi]})
+        own_equal = torch.equal(g["pred_vertices"][lo:hi], local["pred_vertices"])
+        q.put((rank, None, errs, own_equal, tuple(got["cls_logits_softmax_local"].shape)))
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc(), {}, False, ()))
+
+
+@pytest.mark.parametrize("global_batch,use_graph", [(6, False), (5, True)])
+def test_native_allgather_two_gpus(global_batch, use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, global_batch, use_graph)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, errs, own_equal, lshape in res:
+        assert err is None, err
+        # the other rank's rows were computed with a different batch size (different GEMM tile shapes): accumulation noise
+        assert all(v < 1e-3 for v in errs.values()), errs
+        assert own_equal
+        assert lshape[0] in (global_batch // 2, global_batch - global_batch // 2)

@@ -34,7 +34,7 @@ class Config(Structure):
                 ("cls_token_inter", c_int), ("cls_blocks", c_int),
                 ("code_dim", c_int), ("tok_width", c_int), ("tok_depth", c_int), ("tok_dilation_rate", c_int),
                 ("tok_joints", c_int), ("n_upsample", c_int), ("upsample_sizes", c_int * 8),
-                ("focal_length", c_float)]
+                ("focal_length", c_float), ("strict", c_int)]
 
 
 class VitBlock(Structure):
@@ -158,6 +158,12 @@ SIGNATURES = {
     "thmr_engine_profile": (c_int, [c_void_p, c_void_p, c_int, POINTER(Outputs), c_void_p, c_void_p,
                                     POINTER(c_float), c_int]),
     "thmr_engine_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "thmr_comm_unique_id": (c_int, [c_void_p]),
+    "thmr_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "thmr_comm_destroy": (None, [c_void_p]),
+    "thmr_comm_nranks": (c_int, [c_void_p]),
+    "thmr_comm_rank": (c_int, [c_void_p]),
+    "thmr_allgather_outputs": (c_int, [c_void_p, c_void_p, POINTER(Outputs), c_int, c_void_p]),
 }
 
 

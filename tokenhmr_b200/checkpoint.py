@@ -202,6 +202,70 @@ def merge_state_dicts(model_sd: Dict[str, torch.Tensor], tokenizer_net: Dict[str
     return out
 
 
+def _unsupported(what: str, got, want, ref: str):
+    from ._lib import ThmrError
+    raise ThmrError(f"unsupported configuration: {what} = {got!r}; this engine implements {want} only ({ref})")
+
+
+def validate_model_config(y: Dict[str, Any]) -> None:
+    """Reject every reference variant the engine does not implement instead of silently running the release path.
+    Defaults are the reference's own `.get()` defaults."""
+    m = y.get("MODEL", {}) or {}
+    head = m.get("SMPL_HEAD", {}) or {}
+    # build_smpl_head (heads/__init__.py:4-13): default 'hmr' raises in the reference too; only 'token' is built here
+    if "SMPL_HEAD" in m and head.get("TYPE", "hmr") != "token":
+        _unsupported("MODEL.SMPL_HEAD.TYPE", head.get("TYPE", "hmr"), "'token' (SMPLTokenDecoderHead)", "heads/__init__.py:4-13")
+    if int(head.get("IEF_ITERS", 1)) != 1:
+        _unsupported("MODEL.SMPL_HEAD.IEF_ITERS", head.get("IEF_ITERS"), "1 iteration", "token_head.py:86")
+    if head.get("TRANSFORMER_INPUT", "zero") != "zero":
+        _unsupported("MODEL.SMPL_HEAD.TRANSFORMER_INPUT", head.get("TRANSFORMER_INPUT"), "'zero' (constant query token)",
+                     "token_head.py:29,88-91")
+    if head.get("JOINT_REP", "6d") != "6d":
+        _unsupported("MODEL.SMPL_HEAD.JOINT_REP", head.get("JOINT_REP"), "'6d'", "token_head.py:23-24")
+    tk = head.get("TOKENIZER", {}) or {}
+    if tk.get("TOKENIZER_TYPE", "Vanilla") not in ("Vanilla",):
+        _unsupported("MODEL.SMPL_HEAD.TOKENIZER.TOKENIZER_TYPE", tk.get("TOKENIZER_TYPE"), "'Vanilla'",
+                     "token_classifier.py:12-20")
+    dec = head.get("TRANSFORMER_DECODER", {}) or {}
+    if dec.get("norm", "layer") != "layer":
+        _unsupported("TRANSFORMER_DECODER.norm", dec.get("norm"), "'layer'", "pose_transformer.py:33-37")
+    if int(dec.get("context_dim", 1280)) != 1280 or int(dec.get("dim", 1024)) != 1024:
+        _unsupported("TRANSFORMER_DECODER.context_dim/dim", (dec.get("context_dim"), dec.get("dim")), "1280 / 1024",
+                     "tokenhmr_release.yaml:73-81")
+    if int(dec.get("dim_head", 64)) != 64 or int(dec.get("heads", 8)) > 8:
+        _unsupported("TRANSFORMER_DECODER.dim_head/heads", (dec.get("dim_head"), dec.get("heads")), "<= 8 heads x 64",
+                     "tokenhmr_release.yaml:73-81")
+    bb = m.get("BACKBONE", {}) or {}
+    if bb.get("TYPE", "vit") != "vit":
+        _unsupported("MODEL.BACKBONE.TYPE", bb.get("TYPE"), "'vit' (ViT-H/16)", "backbones/__init__.py")
+    smpl = y.get("SMPL", {}) or {}
+    if smpl.get("update_hips", smpl.get("UPDATE_HIPS", False)):
+        _unsupported("SMPL.update_hips", True, "False", "smpl_wrapper.py:33-36")
+    if int(smpl.get("NUM_BODY_JOINTS", 23)) != 23:
+        _unsupported("SMPL.NUM_BODY_JOINTS", smpl.get("NUM_BODY_JOINTS"), "23", "tokenhmr_release.yaml:31-37")
+    if (smpl.get("GENDER", "neutral") or "neutral") not in ("neutral", "male", "female"):
+        _unsupported("SMPL.GENDER", smpl.get("GENDER"), "an SMPL .pkl gender", "smpl_wrapper.py:10")
+
+
+def validate_against_weights(cfg: TokenHMRConfig, sd: Dict[str, torch.Tensor], smpl: Dict[str, torch.Tensor]) -> None:
+    """Shapes the files imply must agree with the configuration the engine is built for."""
+    from ._lib import ThmrError
+    cb = sd.get("tokenizer.quantizer.codebook")
+    if cb is not None and tuple(cb.shape) != (cfg.token_class_num, cfg.code_dim):
+        raise ThmrError(f"tokenizer codebook is {tuple(cb.shape)} but the classifier predicts {cfg.token_class_num} classes "
+                        f"of dimension {cfg.code_dim} (TOKEN_CLASS_NUM / TOKEN_CODE_DIM vs tokenizer NB_CODE / CODE_DIM)")
+    if cfg.nb_code != cfg.token_class_num:
+        raise ThmrError(f"tokenizer NB_CODE {cfg.nb_code} != MODEL.SMPL_HEAD.TOKENIZER.TOKEN_CLASS_NUM {cfg.token_class_num}")
+    te = sd.get("smpl_head.transformer.to_token_embedding.weight")
+    if te is not None and te.shape[1] != 1:
+        raise ThmrError(f"to_token_embedding takes {te.shape[1]} inputs: a TRANSFORMER_INPUT='mean_shape' checkpoint "
+                        "(token_head.py:29-33) is not supported")
+    if "joint_regressor_extra" not in smpl:
+        import warnings
+        warnings.warn("no joint_regressor_extra (SMPL_to_J19.pkl): pred_keypoints_3d/2d will have 25 instead of 44 joints "
+                      "(smpl_wrapper.py:22-23,37-39)")
+
+
 def config_from_files(model_cfg_yaml: Optional[str], arch: Optional[Dict[str, Any]] = None) -> TokenHMRConfig:
     """model_config.yaml (MODEL.* of the yacs dump, models/__init__.py:6-17) + tokenizer hparams -> TokenHMRConfig."""
     kw: Dict[str, Any] = {}
@@ -209,6 +273,7 @@ def config_from_files(model_cfg_yaml: Optional[str], arch: Optional[Dict[str, An
         import yaml
         with open(model_cfg_yaml) as f:
             y = yaml.safe_load(f) or {}
+        validate_model_config(y)
         m = y.get("MODEL", {})
         if "IMAGE_SIZE" in m:
             kw["image_size"] = int(m["IMAGE_SIZE"])
@@ -256,4 +321,5 @@ def load_tokenhmr(checkpoint_path: str, model_cfg: Optional[str] = None, tokeniz
     blocks = {int(m.group(1)) for k in sd for m in [re.match(r"backbone\.blocks\.(\d+)\.", k)] if m}
     cfg = dataclasses.replace(cfg, vit_depth=max(blocks) + 1 if blocks else cfg.vit_depth,
                               num_verts=int(smpl["v_template"].shape[0]))
+    validate_against_weights(cfg, sd, smpl)
     return TokenHMREngine(cfg, sd, smpl, device=device, **engine_kw), cfg

@@ -50,7 +50,7 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __half* __res
 // LayerNorm over the last dimension (nn.LayerNorm: biased variance, eps inside the sqrt).
 //   x (R,C) fp32 -> y16 (fp16, nullable) and/or y32 (fp32, nullable); optional ReLU (FCBlock, modules.py:15-19).
 //   One warp per row; the row lives in registers (C <= 32*4*VEC4 elements), two-pass statistics.
-//   out_t > 0: fp16 output written transposed inside groups of out_t rows:
+//   out_t > 0: outputs (fp16 and fp32) written transposed inside groups of out_t rows:
 //       y16[(r / T) * C * T + c * T + (r % T)]   (MixerLayer token mixing, modules.py:56-59)
 //   Row pitch of the fp16 output is ld16 (elements) when not transposed.
 // ------------------------------------------------------------------------------------------------
@@ -118,7 +118,17 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         o.z = (v[i].z - mean) * rstd * g.z + bb.z;
         o.w = (v[i].w - mean) * rstd * g.w + bb.w;
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (y32) *reinterpret_cast<float4*>(y32 + static_cast<size_t>(warp) * C + c) = o;
+        if (y32) {
+          if (out_t > 0) {   // transposed inside groups of out_t rows, like the fp16 output (strict mode operand)
+            float* base = y32 + static_cast<size_t>(warp / out_t) * C * out_t + (warp % out_t);
+            base[static_cast<size_t>(c) * out_t] = o.x;
+            base[static_cast<size_t>(c + 1) * out_t] = o.y;
+            base[static_cast<size_t>(c + 2) * out_t] = o.z;
+            base[static_cast<size_t>(c + 3) * out_t] = o.w;
+          } else {
+            *reinterpret_cast<float4*>(y32 + static_cast<size_t>(warp) * C + c) = o;
+          }
+        }
         if (y16) {
           if (out_t > 0) {
             __half* base = y16 + static_cast<size_t>(warp / out_t) * C * out_t + (warp % out_t);

@@ -118,6 +118,7 @@ struct thmr_engine {
   int B = 0;
   std::vector<thmr::Step> steps;
   size_t vit_steps = 0;  // steps [0, vit_steps) = backbone
+  int launches = 0;      // kernels per forward (strict mode counts them while building; 0 = default-path formula)
 };
 
 namespace thmr {

@@ -45,9 +45,8 @@ inline int pick_epi(const GemmDesc& d) {
                      d.M >= kGemmBM && (!d.bias || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
   if (!plain) return kEpiGeneric;
   if (d.out16 && !d.out32 && !d.resid && d.ld16 % 8 == 0 && d.N % 8 == 0 && d.alpha == 1.0f) return kEpiStore16;
-  if (d.out32 && !d.out16 && d.resid == d.out32 && d.ldr == d.ld32 && d.act == kActNone && d.ld32 % 4 == 0 &&
-      d.alpha == 1.0f)
-    return kEpiAdd32;
+  if (d.out32 && !d.out16 && d.resid == d.out32 && d.ldr == d.ld32 && d.act == kActNone && d.ld32 % 4 == 0)
+    return kEpiAdd32;      // alpha * acc + bias reduce-added into the output
   if (d.out32 && !d.out16 && !d.resid && d.act == kActNone && d.ld32 % 4 == 0) return kEpiStore32;
   return kEpiGeneric;
 }

@@ -3,8 +3,10 @@
 #include <algorithm>
 #include <new>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "engine.cuh"
+#include "engine_strict.cuh"
 #include "eval_kernels.cuh"
 #include "preproc.cuh"
 #include "tok_encoder.cuh"
@@ -36,7 +38,7 @@ int dev_clone(T** p, const T* src, size_t n) {
 
 extern "C" {
 
-int thmr_abi_version(void) { return 3; }
+int thmr_abi_version(void) { return 4; }
 
 const char* thmr_last_error(void) { return last_error_buf(); }
 
@@ -48,6 +50,12 @@ int thmr_check_device_flags(void) {
     unsigned int zero = 0;
     THMR_CUDA(cudaMemcpyToSymbol(g_pipeline_timeout, &zero, sizeof(zero)));
     return fail(THMR_ERR_TIMEOUT, "device pipeline wait timed out (mbarrier never completed)");
+  }
+  THMR_CUDA(cudaMemcpyFromSymbol(&flag, g_strict_overflow, sizeof(flag)));
+  if (flag) {
+    unsigned int zero = 0;
+    THMR_CUDA(cudaMemcpyToSymbol(g_strict_overflow, &zero, sizeof(zero)));
+    return fail(THMR_ERR_INVALID, "strict mode: an activation left the split-fp16 range (|a| >= 4094 or NaN)");
   }
   return THMR_OK;
 }
@@ -550,6 +558,7 @@ void thmr_engine_destroy(thmr_engine* e) { delete e; }
 size_t thmr_engine_workspace_bytes(const thmr_engine* e, int max_batch) {
   if (!e || max_batch <= 0) return 0;
   int st;
+  if (e->cfg.strict) return engine_build_strict(const_cast<thmr_engine*>(e), nullptr, max_batch, false, &st, nullptr);
   return engine_build(const_cast<thmr_engine*>(e), nullptr, max_batch, false, &st, nullptr);
 }
 
@@ -559,7 +568,8 @@ static int engine_prepare(thmr_engine* e, int B, void* workspace, cudaStream_t s
   if (e->ws != workspace || e->B != B) {
     int status = THMR_OK;
     e->ws = nullptr;
-    engine_build(e, workspace, B, true, &status, st);
+    if (e->cfg.strict) engine_build_strict(e, workspace, B, true, &status, st);
+    else engine_build(e, workspace, B, true, &status, st);
     if (status != THMR_OK) { e->steps.clear(); return status; }
     e->ws = workspace;
     e->B = B;
@@ -623,7 +633,77 @@ int thmr_engine_profile(thmr_engine* e, const float* img, int B, const thmr_outp
 int thmr_engine_num_launches(const thmr_engine* e) {
   if (!e) return 0;
   // every step is one kernel except the SMPL tail (assemble + pose + blend GEMM + skin + joints = 5)
+  if (e->cfg.strict) return e->launches;
   return e->steps.empty() ? 0 : static_cast<int>(e->steps.size()) + 4;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU exchange
+int thmr_comm_unique_id(void* id128) {
+  THMR_CHECK(id128, "comm_unique_id: null argument");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(THMR_ERR_CUDA, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "no error text");
+  NcclUniqueId id;
+  THMR_NCCL(api, api->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return THMR_OK;
+}
+
+int thmr_comm_create(const void* id128, int nranks, int rank, thmr_comm** out) {
+  THMR_CHECK(id128 && out, "comm_create: null argument");
+  THMR_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "comm_create: rank %d of %d", rank, nranks);
+  NcclApi* api = nccl_api();
+  if (!api) return fail(THMR_ERR_CUDA, "libnccl.so.2 could not be loaded");
+  thmr_comm* c = new (std::nothrow) thmr_comm();
+  if (!c) return fail(THMR_ERR_NOMEM, "comm_create: out of host memory");
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  THMR_CUDA(cudaGetDevice(&c->device));
+  const int r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) {
+    delete c;
+    return fail(THMR_ERR_CUDA, "ncclCommInitRank(rank %d of %d) failed: %s", rank, nranks, api->GetErrorString(r));
+  }
+  c->nranks = nranks;
+  c->rank = rank;
+  *out = c;
+  return THMR_OK;
+}
+
+void thmr_comm_destroy(thmr_comm* c) {
+  if (!c) return;
+  NcclApi* api = nccl_api();
+  if (api && c->comm) api->CommDestroy(c->comm);
+  delete c;
+}
+
+int thmr_comm_nranks(const thmr_comm* c) { return c ? c->nranks : 0; }
+int thmr_comm_rank(const thmr_comm* c) { return c ? c->rank : -1; }
+
+int thmr_allgather_outputs(const thmr_engine* e, thmr_comm* c, const thmr_outputs* g, int rows, void* stream) {
+  THMR_CHECK(e && c && g && rows > 0, "allgather_outputs: bad argument");
+  NcclApi* api = nccl_api();
+  THMR_CHECK(api && c->comm, "allgather_outputs: communicator not initialised");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nj = 25 + e->smpl->m.n_extra;
+  struct Field { float* base; size_t per_image; };
+  const Field fields[] = {
+      {g->pred_vertices, static_cast<size_t>(e->smpl->m.V) * 3},
+      {g->pred_keypoints_3d, static_cast<size_t>(nj) * 3},
+      {g->pred_keypoints_2d, static_cast<size_t>(nj) * 2},
+      {g->pred_cam, 3}, {g->pred_cam_t, 3}, {g->focal_length, 2},
+      {g->rotmats, 24 * 9}, {g->betas, static_cast<size_t>(e->smpl->m.nb)},
+      {g->cls_logits_softmax, static_cast<size_t>(e->cfg.token_num) * e->cfg.token_class_num},
+  };
+  THMR_NCCL(api, api->GroupStart());
+  int status = THMR_OK;
+  for (const Field& f : fields) {
+    if (!f.base) continue;
+    const size_t count = f.per_image * rows;
+    const int r = api->AllGather(f.base + count * c->rank, f.base, count, kNcclFloat32, c->comm, st);
+    if (r != 0 && status == THMR_OK) status = fail(THMR_ERR_CUDA, "ncclAllGather failed: %s", api->GetErrorString(r));
+  }
+  THMR_NCCL(api, api->GroupEnd());
+  return status;
 }
 
 }  // extern "C"

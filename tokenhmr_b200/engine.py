@@ -15,7 +15,7 @@ if the library is missing.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional
+from typing import Dict, NamedTuple, Optional
 
 import torch
 import torch.nn as nn
@@ -25,6 +25,20 @@ from ._lib import check, lib
 from .config import TokenHMRConfig
 from .ops import SMPLModel
 from .weights import PackedWeights, make_config_struct
+
+
+class ShardSpec(NamedTuple):
+    """How this rank's forward sits in a batch sharded over `world` GPUs (tokenhmr_b200.dist.ShardedTokenHMR):
+    every gathered output is one buffer of world * rows images, this rank writes rows [rank*rows, rank*rows + B)."""
+    comm: int            # thmr_comm* (ctypes handle value)
+    world: int
+    rank: int
+    rows: int            # rows reserved per rank (>= the largest local batch)
+    gather_logits: bool = False
+
+
+GATHERED_FIELDS = ("pred_vertices", "pred_keypoints_3d", "pred_keypoints_2d", "pred_cam", "pred_cam_t", "focal_length",
+                   "rotmats", "betas")
 
 
 class _SmplFacade:
@@ -37,18 +51,32 @@ class _SmplFacade:
 
 class TokenHMREngine(nn.Module):
     def __init__(self, cfg: TokenHMRConfig, state_dict: Dict[str, torch.Tensor], smpl: Dict[str, torch.Tensor],
-                 device: str | torch.device = "cuda:0", max_batch: int = 64, use_cuda_graph: bool = True):
+                 device: str | torch.device = "cuda:0", max_batch: int = 256, use_cuda_graph: bool = True,
+                 strict: bool = False, alias_outputs: bool = False, max_cached_shapes: int = 6):
+        """strict: every contraction of the path in split-fp16 (3 tensor-core products, ~2^-21 relative: fp32-grade)
+        instead of fp16 operands -- the mode whose results match the fp32 reference to 1e-4 with identical pose tokens
+        (DESIGN.md §2); about 4x slower.  alias_outputs: return views of the engine's static output buffers (valid until
+        the next forward of the same batch size / slot) instead of fresh tensors; TokenHMRPipeline uses it.
+        max_batch: largest batch a forward accepts (bounds the workspace).  max_cached_shapes: distinct (batch size, slot)
+        buffer sets kept alive; the least recently used one is dropped beyond that."""
         super().__init__()
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.ThmrError("TokenHMREngine needs a CUDA device (there is no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         lib()  # fail now if the shared library is missing
+        from .checkpoint import validate_against_weights
+        validate_against_weights(cfg, state_dict, smpl)
+        self.strict = bool(strict)
+        self.alias_outputs = bool(alias_outputs)
+        self.max_cached_shapes = int(max_cached_shapes)
         with torch.cuda.device(self.device):
-            self.weights = PackedWeights(state_dict, cfg, self.device)
+            self.weights = PackedWeights(state_dict, cfg, self.device, strict=self.strict)
             self.smpl_model = SMPLModel(smpl, self.device)
             self.smpl = _SmplFacade(self.smpl_model)
-            self._cfg_struct = make_config_struct(cfg)
+            self._cfg_struct = make_config_struct(cfg, strict=self.strict)
             h = ctypes.c_void_p()
             check(lib().thmr_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self.weights.struct),
                                            self.smpl_model.handle, ctypes.byref(h)))
@@ -67,17 +95,56 @@ class TokenHMREngine(nn.Module):
         except Exception:
             pass
 
-    def to(self, *args, **kwargs):  # weights are already resident on self.device
+    def to(self, *args, **kwargs):
+        """The packed weights live on the device given at construction: `.to(that device)` (demo.py:35, eval.py:52) is a
+        no-op, any other device or a dtype change raises instead of being silently ignored."""
+        dev, dtype = None, kwargs.get("dtype")
+        for a in list(args) + [kwargs.get("device")]:
+            if isinstance(a, (str, torch.device, int)) and not isinstance(a, bool):
+                dev = torch.device("cuda", a) if isinstance(a, int) else torch.device(a)
+            elif isinstance(a, torch.dtype):
+                dtype = a
+            elif isinstance(a, torch.Tensor):
+                dev, dtype = a.device, a.dtype
+        if dev is not None:
+            if dev.type == "cuda" and dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            if dev != self.device:
+                raise _lib.ThmrError(f"TokenHMREngine lives on {self.device}; .to({dev}) is not supported "
+                                     "(build a new engine on that device; there is no CPU path)")
+        if dtype is not None and dtype != torch.float32:
+            raise _lib.ThmrError(f".to({dtype}): the engine's numeric contract is fixed (fp32 in / fp32 out)")
         return self
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else
+                                    (device if isinstance(device, int) else torch.device(device).index or 0)))
+
+    def half(self):
+        return self.to(torch.float16)
 
     def num_launches(self) -> int:
         return lib().thmr_engine_num_launches(self._h)
 
-    def _state(self, B: int, taps: bool, slot: int = 0) -> dict:
-        key = (B, int(taps), slot)
+    def _state(self, B: int, taps: bool, slot: int = 0, shard: Optional[ShardSpec] = None) -> dict:
+        if B > self.max_batch:
+            raise _lib.ThmrError(f"batch of {B} images exceeds max_batch={self.max_batch} (raise it at construction)")
+        if shard is not None and not (0 < B <= shard.rows and 0 <= shard.rank < shard.world):
+            raise _lib.ThmrError(f"shard {shard} cannot hold a local batch of {B}")
+        key = (B, int(taps), slot) + ((shard.world, shard.rank, shard.rows, shard.gather_logits) if shard else ())
         st = self._bufs.get(key)
         if st is not None:
+            self._bufs[key] = self._bufs.pop(key)          # most recently used last
             return st
+        while len(self._bufs) >= max(1, self.max_cached_shapes):
+            # drop the least recently used buffer set (its workspace, outputs and graph); the engine's plan cache is
+            # keyed on the workspace pointer, so forget it if it pointed there
+            old_key = next(iter(self._bufs))
+            torch.cuda.synchronize(self.device)
+            self._bufs.pop(old_key)
         c, dev = self.cfg, self.device
         nj = 25 + self.smpl_model.n_extra
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
@@ -90,6 +157,16 @@ class TokenHMREngine(nn.Module):
         }
         if taps:
             t.update({"vit_tokens": f(B, c.num_tokens, c.vit_dim), "token_out": f(B, c.dec_dim), "pose6d": f(B, 144)})
+        g, gouts = None, None
+        if shard is not None:
+            # in-place all-gather layout: one buffer of world * rows images per gathered field; the engine writes this
+            # rank's images straight into its rows (no pack / unpack copies)
+            g, gouts = {}, _lib.Outputs()
+            fields = GATHERED_FIELDS + (("cls_logits_softmax",) if shard.gather_logits else ())
+            for name in fields:
+                g[name] = f(shard.world * shard.rows, *t[name].shape[1:])
+                t[name] = g[name][shard.rank * shard.rows: shard.rank * shard.rows + B]
+                setattr(gouts, name, g[name].data_ptr())
         outs = _lib.Outputs()
         for name, _ in _lib.Outputs._fields_:
             if name in t:
@@ -97,25 +174,35 @@ class TokenHMREngine(nn.Module):
         nbytes = lib().thmr_engine_workspace_bytes(self._h, B)
         ws = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
         off = (-ws.data_ptr()) % 1024
-        st = {"t": t, "outs": outs, "ws": ws, "ws_ptr": ws.data_ptr() + off, "graph": None, "warm": False}
+        st = {"t": t, "outs": outs, "ws": ws, "ws_ptr": ws.data_ptr() + off, "graph": None, "warm": False,
+              "g": g, "gouts": gouts, "shard": shard}
         self._bufs[key] = st
         return st
 
     def _launch(self, st: dict, B: int) -> None:
+        stream = torch.cuda.current_stream().cuda_stream
         check(lib().thmr_engine_forward(self._h, st["t"]["img"].data_ptr(), B, ctypes.byref(st["outs"]), st["ws_ptr"],
-                                        torch.cuda.current_stream().cuda_stream))
+                                        stream))
+        sh = st["shard"]
+        if sh is not None and sh.world > 1:
+            # the one exchange of the sharded path: grouped in-place ncclAllGather, same stream (and same CUDA graph)
+            check(lib().thmr_allgather_outputs(self._h, sh.comm, ctypes.byref(st["gouts"]), sh.rows, stream))
 
     @torch.no_grad()
-    def forward(self, batch: Dict, return_taps: bool = False, slot: int = 0) -> Dict:
+    def forward(self, batch: Dict, return_taps: bool = False, slot: int = 0, alias_outputs: Optional[bool] = None,
+                shard: Optional[ShardSpec] = None) -> Dict:
         """TokenHMR.forward: only batch['img'] is read (tokenhmr.py:146).  `slot` selects an independent set of
         input / output / workspace buffers (and CUDA graph), so that a caller can have several forwards in flight
-        (TokenHMRPipeline); the returned tensors alias that slot's buffers until its next forward."""
+        (TokenHMRPipeline).  Like the reference, the returned tensors are fresh (safe to keep across calls) unless
+        alias_outputs is set, in which case they are views of that slot's buffers until its next forward
+        (with `shard`: the gathered fields cover all world * rows images, see tokenhmr_b200.dist)."""
+        alias = self.alias_outputs if alias_outputs is None else alias_outputs
         img = batch["img"]
         if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != self.cfg.image_size or img.shape[3] != self.cfg.image_size:
             raise _lib.ThmrError(f"batch['img'] must be (B,3,{self.cfg.image_size},{self.cfg.image_size}), got {tuple(img.shape)}")
         B = img.shape[0]
         with torch.cuda.device(self.device):
-            st = self._state(B, return_taps, slot)
+            st = self._state(B, return_taps, slot, shard)
             st["t"]["img"].copy_(img.to(torch.float32), non_blocking=True)     # H2D (or D2D) of the batch
             if self.use_cuda_graph:
                 if st["graph"] is None:
@@ -130,7 +217,9 @@ class TokenHMREngine(nn.Module):
                 st["graph"].replay()
             else:
                 self._launch(st, B)
-            t = st["t"]
+            t = dict(st["t"])
+            if st["g"] is not None:
+                t.update(st["g"])           # gathered fields: all world * rows images
             rot = t["rotmats"]
             out = {
                 "cls_logits_softmax": t["cls_logits_softmax"],
@@ -145,6 +234,8 @@ class TokenHMREngine(nn.Module):
             }
             if return_taps:
                 out["_vit_tokens"], out["_token_out"], out["_pred_body_pose_6d"] = t["vit_tokens"], t["token_out"], t["pose6d"]
+            if not alias:
+                out = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
         return out
 
     @torch.no_grad()
@@ -197,8 +288,13 @@ class TokenHMRPipeline:
     the forward and the read-back (e.g. the all-gather of a sharded model)."""
 
     def __init__(self, model: "TokenHMREngine", depth: int = 2, read_back=("pred_vertices", "pred_keypoints_3d",
-                                                                         "pred_cam", "pred_cam_t"), post=None):
+                                                                         "pred_cam", "pred_cam_t"), post=None,
+                 shard: Optional[ShardSpec] = None, read_rows: Optional[slice] = None):
+        """shard: run every forward as this rank's part of a sharded batch (in-place all-gather inside the forward's CUDA
+        graph).  read_rows: rows of each output to copy back to the host (e.g. only this rank's own images when the
+        ranks of one host each hand their shard to the same consumer); default all rows."""
         self.model, self.depth, self.read_back, self.post = model, int(depth), tuple(read_back), post
+        self.shard, self.read_rows = shard, read_rows
         with torch.cuda.device(model.device):
             self.copy_stream = torch.cuda.Stream(model.device)
             self.compute_stream = torch.cuda.Stream(model.device)
@@ -216,7 +312,7 @@ class TokenHMRPipeline:
         m = self.model
         img = batch["img"]
         with torch.cuda.device(m.device):
-            st = m._state(img.shape[0], False, slot)
+            st = m._state(img.shape[0], False, slot, self.shard)
             with torch.cuda.stream(self.copy_stream):
                 if self._used[slot]:
                     self.copy_stream.wait_event(self._done[slot])       # the slot's previous forward has consumed its input
@@ -224,14 +320,16 @@ class TokenHMRPipeline:
                 self._copied[slot].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self._copied[slot])
-                out = m.forward({"img": st["t"]["img"]}, slot=slot)   # the D2D self-copy of the input is a no-op
+                out = m.forward({"img": st["t"]["img"]}, slot=slot, alias_outputs=True,   # (input self-copy: a no-op)
+                                shard=self.shard)
                 if self.post is not None:
                     out = self.post(out)
                 host = self._host[slot]
                 for k in self.read_back:
-                    if k not in host or host[k].shape != out[k].shape:
-                        host[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
-                    host[k].copy_(out[k], non_blocking=True)
+                    src = out[k] if self.read_rows is None else out[k][self.read_rows]
+                    if k not in host or host[k].shape != src.shape:
+                        host[k] = torch.empty(src.shape, dtype=src.dtype).pin_memory()
+                    host[k].copy_(src, non_blocking=True)
                 self._done[slot].record(self.compute_stream)
             self._used[slot] = True
         return ticket

@@ -32,17 +32,41 @@ def strip_checkpoint(state_dict: Dict[str, torch.Tensor], tokenizer_net: Dict[st
     return out
 
 
+STRICT_W_SCALE = 256.0     # kStrictWScale (csrc/strict.cuh)
+
+
 class PackedWeights:
     """Owns the device tensors the engine points into (must outlive the engine)."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], cfg: TokenHMRConfig, device: torch.device):
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: TokenHMRConfig, device: torch.device, strict: bool = False):
+        """strict: matrices are packed for the split-fp16 GEMMs of strict mode (csrc/strict.cuh): f16 [out, 3*in] =
+        [hi | hi | lo] of w * 2^8 with hi = fp16(w * 2^8), lo = fp16(w * 2^8 - hi); conv weights per tap."""
         self.cfg = cfg
         self.device = device
+        self.strict = bool(strict)
         self._keep: List[torch.Tensor] = []
         g = lambda n: sd[n]
 
-        def f16(t: torch.Tensor) -> int:
-            t = t.detach().to(device=device, dtype=torch.float16).contiguous()
+        def split_w(t: torch.Tensor, taps: int = 1) -> torch.Tensor:
+            """[out, taps*in] fp32 -> [out, taps*3*in] fp16, per tap [hi | hi | lo] of w * STRICT_W_SCALE."""
+            t = t.detach().to(device=device, dtype=torch.float32)
+            amax = float(t.abs().max()) if t.numel() else 0.0
+            if not amax < 65504.0 / STRICT_W_SCALE:
+                raise _lib.ThmrError(f"strict mode: weight magnitude {amax:g} exceeds the split-fp16 range "
+                                     f"(|w| < {65504.0 / STRICT_W_SCALE:g})")
+            ws = t * STRICT_W_SCALE
+            hi = ws.to(torch.float16)
+            lo = (ws - hi.to(torch.float32)).to(torch.float16)
+            out_f, k = t.shape
+            cin = k // taps
+            hi3, lo3 = hi.view(out_f, taps, cin), lo.view(out_f, taps, cin)
+            return torch.cat([hi3, hi3, lo3], dim=2).reshape(out_f, taps * 3 * cin).contiguous()
+
+        def f16(t: torch.Tensor, taps: int = 1) -> int:
+            if self.strict:
+                t = split_w(t, taps)
+            else:
+                t = t.detach().to(device=device, dtype=torch.float16).contiguous()
             self._keep.append(t)
             return t.data_ptr()
 
@@ -55,7 +79,7 @@ class PackedWeights:
             w = g(prefix + ".weight")                      # [Cout, Cin, k]
             cout, cin, k = w.shape
             wt = w.permute(0, 2, 1).reshape(cout, k * cin)  # tap-major: column = tap*Cin + c
-            return _lib.Conv(f16(wt), f32(g(prefix + ".bias")))
+            return _lib.Conv(f16(wt, taps=k), f32(g(prefix + ".bias")))
 
         W = _lib.Weights()
         D = cfg.vit_dim
@@ -141,8 +165,9 @@ class PackedWeights:
         return sum(t.numel() * t.element_size() for t in self._keep)
 
 
-def make_config_struct(cfg: TokenHMRConfig) -> _lib.Config:
+def make_config_struct(cfg: TokenHMRConfig, strict: bool = False) -> _lib.Config:
     c = _lib.Config()
+    c.strict = 1 if strict else 0
     for f in ("image_size", "crop_w", "patch", "patch_pad", "vit_dim", "vit_depth", "vit_heads", "vit_mlp_ratio",
               "vit_ln_eps", "dec_dim", "dec_depth", "dec_heads", "dec_dim_head", "dec_mlp_dim", "ln_eps", "token_num",
               "token_class_num", "cls_hidden", "cls_hidden_inter", "cls_token_inter", "cls_blocks", "code_dim",
