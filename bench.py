@@ -34,10 +34,16 @@ FLOP_PER_IMAGE = 252.10e9
 PER_GPU_BATCH = 64
 
 
+def _profile_json(stem: str):
+    """Newest committed profiles/r<N>_<stem>.json (None when absent)."""
+    cands = sorted((ROOT / "profiles").glob(f"r*_{stem}.json"))
+    return cands[-1] if cands else None
+
+
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
-    `ncu --set full` capture, scripts/make_profiles.sh -> profiles/r1_traffic.json); None when no capture is committed."""
-    p = ROOT / "profiles" / "r1_traffic.json"
+    `ncu --set full` capture, scripts/make_profiles.sh -> profiles/r<N>_traffic.json); None when no capture is committed."""
+    p = _profile_json("traffic")
     try:
         d = json.loads(p.read_text())
         return {"bytes_per_launch": d["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
@@ -142,10 +148,23 @@ def cpu_forward_rate(budget_s: float = 15.0):
     return n / dt, n, dt, threads
 
 
+WORKLOAD = "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)"
+
+
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": world * PER_GPU_BATCH,
+            "parallelism": f"dp{world} + 1 all-gather of outputs", "weights": "random-init release architecture (seed 1234)",
+            "l2": "1.4 GB of fp16 weights + 0.6 GB of activations stream through the 126 MB L2 every step (inputs larger "
+                  "than L2, no flush needed)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path.  /root/reference does not exist on the GPU box and the
     reference package cannot be installed offline (pytorch_lightning / smplx / yacs missing), so this
-    times the oracle port, which is bit-identical to the reference modules (tests/test_oracle_pinned.py)."""
+    times the oracle port, which is bit-identical to the reference modules (tests/test_oracle_pinned.py).  Each step
+    is a bounded sample of the bs=64 batch (stated in cpu_baseline.sample), sized from a 4-image probe so that the whole
+    --steps / --warmup run stays within a few minutes; the rate is per image."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -157,14 +176,13 @@ def run_reference(args):
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
     threads = pick_cpu_threads(sd, smpl, cfg)
     torch.set_num_threads(threads)
-    # images per step: a bounded sample of the bs=64 workload, sized from a 4-image probe so that one step is ~10 s of
-    # CPU work on this host (4..64 images)
     with torch.no_grad():
         probe = synth.make_images(4, cfg)
         t = time.perf_counter()
         O.forward(sd, smpl, probe, cfg)
         t4 = time.perf_counter() - t
-    sample = max(4, min(64, int(10.0 / t4 * 4) // 4 * 4))
+    budget_s = 240.0 / max(1, args.steps + args.warmup)          # whole run ~4 minutes
+    sample = max(4, min(PER_GPU_BATCH, int(budget_s / t4 * 4) // 4 * 4))
     img = synth.make_images(sample, cfg)
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -176,24 +194,87 @@ def run_reference(args):
     value = sample * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)",
-                   "sample": f"{sample} images per step"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * PER_GPU_BATCH / sample,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} images/step x {args.steps} steps, fp32 eager torch, best of 8/16/32/64/all host threads ({os.cpu_count()} available)"},
+                         "sample": f"{sample} of the 64 images per step x {args.steps} steps (ms_per_step is scaled to 64 "
+                                   f"images), fp32 eager torch, best of 8/16/32/64/all host threads ({os.cpu_count()} available)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
+def cuda_time(fn, n=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def standalone_configs(dev, peaks) -> dict:
+    """BASELINE.json configs 1, 4 and 5 (1-based as SURVEY.md section 8d numbers them) under the same clock as the headline:
+    CPU bs=1 forward (oracle port), VQ nearest-code arg-min 1 M x 2048 x 256, SMPL lbs() 4096 poses."""
+    import torch
+    from oracle import tokenhmr_oracle as O
+    from tokenhmr_b200 import ops, synth
+    from tokenhmr_b200.config import release_config
+    cfg = release_config()
+    out = {}
+    # config 4: VQ arg-min (quantize_cnn.py:80-86); inputs larger than L2 (1 GB of queries)
+    cb = torch.randn(2048, 256, device=dev, generator=torch.Generator(dev).manual_seed(1))
+    x = torch.randn(1_000_000, 256, device=dev, generator=torch.Generator(dev).manual_seed(2))
+    ms = cuda_time(lambda: ops.vq_quantize(x, cb))
+    pick = torch.randint(0, 2048, (100_000,), device=dev)
+    near = cb[pick] + 0.05 * torch.randn(100_000, 256, device=dev)
+    traffic = _profile_json("vq_traffic")
+    out["vq_argmin_1M_x_2048_x_256"] = {
+        "ms": ms, "queries_per_s": 1e6 / (ms * 1e-3), "algorithmic_tflops": 2 * 1e6 * 2048 * 256 / (ms * 1e-3) / 1e12,
+        "tensor_tflops_incl_3x_split": 3 * 2 * 1e6 * 2048 * 256 / (ms * 1e-3) / 1e12,
+        "algorithmic_bytes": 1.034e9, "algorithmic_gbs": 1.034 / (ms * 1e-3),
+        "dram_bytes_ncu": (json.loads(traffic.read_text()) if traffic else None),
+        "exact_on_near_code_queries": bool(torch.equal(ops.vq_quantize(near, cb), pick)), "l2": "1 GB of queries > L2"}
+    del x, near
+    # config 5: LBS 4096 poses (smplx lbs as restated in oracle/smpl_oracle.py), pose2rot=True
+    m = ops.SMPLModel(synth.make_smpl(cfg), dev)
+    aa = 0.3 * torch.randn(4096, 24, 3, device=dev)
+    be = torch.randn(4096, 10, device=dev)
+    ms = cuda_time(lambda: m.lbs(be, aa))
+    out["smpl_lbs_4096_poses"] = {"ms": ms, "poses_per_s": 4096 / (ms * 1e-3), "algorithmic_gbs": 4096 * 84.1e3 / (ms * 1e-3) / 1e9,
+                                  "hbm_gbs_peak": peaks["hbm_gbs"], "frac_of_hbm": 4096 * 84.1e3 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                  "l2": "344 MB of outputs > L2"}
+    # config 1: the reference's CPU path at bs=1 (oracle port, all host threads the probe found best)
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    threads = pick_cpu_threads(sd, smpl, cfg)
+    torch.set_num_threads(threads)
+    img1 = synth.make_images(1, cfg)
+    with torch.no_grad():
+        O.forward(sd, smpl, img1, cfg)
+        ts = []
+        for _ in range(3):
+            t = time.perf_counter()
+            O.forward(sd, smpl, img1, cfg)
+            ts.append(time.perf_counter() - t)
+    out["cpu_reference_bs1"] = {"ms": sorted(ts)[1] * 1e3, "images_per_s": 1.0 / sorted(ts)[1], "cores": threads,
+                                "kind": "port", "runs": 3}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the standalone configs and the strict-mode rate")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -202,23 +283,24 @@ def main():
     import torch
     import torch.distributed as dist
     from tokenhmr_b200 import synth
-    from tokenhmr_b200._lib import lib
     from tokenhmr_b200.config import release_config
     from tokenhmr_b200.dist import ShardedTokenHMR
-    from tokenhmr_b200.engine import TokenHMREngine
+    from tokenhmr_b200.engine import TokenHMREngine, TokenHMRPipeline
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    os.environ.pop("NCCL_DEBUG", None)     # keep stdout to the single JSON line (any NCCL_DEBUG level prints the version)
+    # NCCL_DEBUG is left alone: its log is the evidence for rank count and transport (the JSON line is printed last)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     cfg = release_config()
     B = PER_GPU_BATCH
-    model = TokenHMREngine(cfg, synth.make_state_dict(cfg), synth.make_smpl(cfg), device=dev, use_cuda_graph=True)
-    sharded = ShardedTokenHMR(model)
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    model = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True)
+    sharded = ShardedTokenHMR(model) if world > 1 else None        # creates the library's own NCCL communicator
+    spec = sharded.spec(B) if sharded else None
     img_host = synth.make_images(B, cfg, seed=rank).pin_memory()
     img_dev = img_host.to(dev)
 
@@ -234,10 +316,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- (1) device-resident throughput: graph replay (+ all-gather when world > 1)
+    # ---- (1) device-resident throughput: ONE CUDA-graph replay per step = forward (+ in-place all-gather when world > 1)
     def step_resident():
-        out = model({"img": img_dev})
-        return sharded.all_gather(out) if world > 1 else out
+        return model.forward({"img": img_dev}, alias_outputs=True, shard=spec)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -266,10 +347,12 @@ def main():
     # TokenHMRPipeline (the streaming driver a dataloader loop uses, engine.py) double-buffers the device-side
     # input / output slots: the H2D of batch i+1 overlaps the forward of batch i.  Every step still copies its own
     # 50 MB input from pinned host memory and reads its own results back; the region is timed from an event in front
-    # of the first H2D (copy stream) to one behind the last D2H (compute stream).
-    from tokenhmr_b200.engine import TokenHMRPipeline
+    # of the first H2D (copy stream) to one behind the last D2H (compute stream).  On N > 1 GPUs every rank reads back
+    # its OWN 64 images (the ranks of one host hand their shards to the same consumer; the gathered buffers stay on
+    # the device for device-side consumers such as the GPU Evaluator).
     consumed = ["pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t"]   # demo.py:80-118, pose_utils.py:217-239
-    pipe = TokenHMRPipeline(model, depth=2, read_back=consumed, post=(sharded.all_gather if world > 1 else None))
+    rows = slice(rank * spec.rows, rank * spec.rows + B) if spec else None
+    pipe = TokenHMRPipeline(model, depth=2, read_back=consumed, shard=spec, read_rows=rows)
 
     def run_e2e(n):
         pending = None
@@ -292,27 +375,50 @@ def main():
     d2h = sum(v.numel() * 4 for v in host_out.values())
 
     # ---- (3) live per-kernel-family accounting (rank 0): timed eager replay of the same forward
-    roofline, families = None, None
+    roofline, families, attention = None, None, None
+    peaks = measured_peaks()
     if rank == 0:
         agg = {}
         for _ in range(3):
             for name, ms, fl, by in model.profile(img_dev):
                 a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
                 a[0] += ms; a[1] += fl; a[2] += by; a[3] += 1
-        peaks = measured_peaks()
         tot_ms = sum(a[0] for a in agg.values())
         families = {k: {"ms_per_step": a[0] / 3, "share": a[0] / tot_ms,
-                        "tflops": (a[1] / (a[0] * 1e-3) / 1e12) if a[1] and a[0] else None} for k, a in agg.items()}
+                        "tflops": (a[1] / (a[0] * 1e-3) / 1e12) if a[1] and a[0] else None,
+                        "gbs": (a[2] / (a[0] * 1e-3) / 1e9) if a[2] and a[0] else None} for k, a in agg.items()}
         gemm = [a for k, a in agg.items() if k.endswith("_gemm")]
         g_ms, g_fl = sum(a[0] for a in gemm), sum(a[1] for a in gemm)
         achieved = g_fl / (g_ms * 1e-3) / 1e12
-        roofline = {"kernel": "gemm_f16_tn_kernel (tcgen05, all ViT/decoder GEMM launches)", "bound": "tensor",
-                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+        roofline = {"kernel": "gemm_f16_tn_2cta_kernel / gemm_f16_tn_kernel (tcgen05, all ViT/decoder GEMM launches)",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
                     "share_of_step": g_ms / tot_ms, "traffic": ncu_traffic(),
                     "whole_step_tflops_per_gpu": B * FLOP_PER_IMAGE / (ms_step * 1e-3) / 1e12}
+        # the second half of BASELINE.json's metric: the fused ViT attention kernel
+        a = agg["vit.attention"]
+        us_layer = a[0] / a[3] * 1e3
+        ncu = _profile_json("attention")
+        attention = {"kernel": "vit_attention3_kernel (S/P/O in TMEM, TS-mode PV)", "us_per_layer_in_step": us_layer,
+                     "tflops": a[1] / (a[0] * 1e-3) / 1e12, "hbm_gbs_algorithmic": a[2] / (a[0] * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": a[2] / (a[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "frac_of_tensor_burst": a[1] / (a[0] * 1e-3) / 1e12 / peaks["tf_burst"],
+                     "ncu": (json.loads(ncu.read_text()) if ncu else None)}
 
-    # ---- (4) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
+    # ---- (4) strict mode (fp32-grade split-fp16 contractions) on the same batch, and the standalone configs
+    strict, standalone = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del pipe
+        sm = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, strict=True)
+        ms = cuda_time(lambda: sm.forward({"img": img_dev}, alias_outputs=True), n=5, warm=3)
+        strict = {"value": B * 1e3 / ms, "unit": "images/s", "ms_per_step": ms, "launches_per_step": sm.num_launches(),
+                  "what": "TokenHMREngine(strict=True): every contraction as a 3-product split-fp16 GEMM, fp32 activations, "
+                          "fp32 CUDA-core attention; vertices within 1e-4 of the fp32 reference, identical pose tokens"}
+        del sm
+        torch.cuda.empty_cache()
+        standalone = standalone_configs(dev, peaks)
+
+    # ---- (5) CPU baseline (rank 0, N=1 only): oracle on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, n, dt, threads = cpu_forward_rate()
@@ -320,24 +426,33 @@ def main():
                "sample": f"{n} of the 64 images, one fp32 eager-torch forward of the oracle ({dt:.1f} s, sized from a "
                          f"4-image probe), thread count picked from 8/16/32/64/{os.cpu_count()}"}
 
+    launches = model.num_launches() + (1 if world > 1 else 0)
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = json.dumps({
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "bs=64 synthetic 256x256 -> 256x192, full TokenHMR forward (ViT-H/16 + token decoder + SMPL)",
-                       "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world} + 1 all-gather of outputs",
-                       "weights": "random-init release architecture (seed 1234)",
-                       "l2": "1.4 GB of fp16 weights + 0.6 GB of activations stream through the 126 MB L2 every step (inputs larger than L2, no flush needed)"},
+            "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "read_back": consumed,
-                    "api": "TokenHMRPipeline.submit/result (depth 2: H2D of the next batch overlaps the forward)"},
-            "gpu_launches": args.steps * model.num_launches(),
-            "launches_per_step": model.num_launches(),
-            "clocks": clocks, "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu,
-        }))
+                    "api": "TokenHMRPipeline.submit/result (depth 2: H2D of the next batch overlaps the forward)"
+                           + ("; each rank reads back its own shard" if world > 1 else "")},
+            "gpu_launches": args.steps * launches, "launches_per_step": launches,
+            "exchange": (None if world == 1 else "thmr_allgather_outputs: 8 grouped in-place ncclAllGather (one NCCL kernel) "
+                         "inside the forward's CUDA graph, library-owned communicator"),
+            "clocks": clocks, "roofline": roofline, "attention": attention, "kernel_families": families,
+            "strict": strict, "standalone": standalone, "cpu_baseline": cpu,
+        })
+    del sharded
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world > 1:
+            time.sleep(1.0)          # let the other ranks' NCCL teardown messages drain: the JSON line stays last
+        sys.stdout.flush()
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

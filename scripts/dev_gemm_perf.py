@@ -1,4 +1,5 @@
-import torch, os
+import torch, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tokenhmr_b200._lib import lib, check
 L = lib(); dev = torch.device("cuda:0"); torch.manual_seed(0)
 st = lambda: torch.cuda.current_stream().cuda_stream

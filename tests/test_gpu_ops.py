@@ -47,10 +47,12 @@ def test_gemm_all_epilogues(cuda_dev, M, N, K, bn):
     assert rel_err(x, ref + resid) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(12288, 1280, 1280), (384, 1280, 1280), (1024, 520, 320), (4608, 1280, 5120), (256, 256, 64)])
+@pytest.mark.parametrize("M,N,K", [(12288, 1280, 1280), (12288, 1280, 5120), (384, 1280, 1280), (1024, 520, 320),
+                                   (4608, 1280, 5120), (256, 256, 64), (9984, 1280, 704)])
 def test_gemm_cta_pair_fp32_epilogues(cuda_dev, M, N, K):
-    """fp32 epilogues (TMA reduce-add, TMA store) of the CTA-pair / CTA-quad kernels at the ViT's proj / fc2 shapes
-    (240 tiles: 3.24 rounds), with fewer tiles than CTA pairs, and with a partial last column tile."""
+    """fp32 epilogues (TMA reduce-add, TMA store) of the CTA-pair kernel at the ViT's proj / fc2 shapes (240 tiles on 74
+    CTA pairs: stream-K, tiles shared by two clusters are reduce-added in a fixed order), with fewer tiles than CTA
+    pairs, with a partial last column tile, and with a k-block count (11) that range boundaries snap against."""
     from tokenhmr_b200._lib import check, lib
     torch.manual_seed(M + N + K)
     A = (torch.randn(M, K, device=cuda_dev) * 0.5).half()
@@ -71,9 +73,14 @@ def test_gemm_cta_pair_fp32_epilogues(cuda_dev, M, N, K):
         return x, y
 
     x, y = run()
-    assert rel_err(x, ref + resid) < 1e-5
-    assert rel_err(y, ref) < 1e-5
+    tol = 1e-5 if K <= 2048 else 3e-5          # fp32 summation-order noise grows with sqrt(K)
+    assert rel_err(x, ref + resid) < tol
+    assert rel_err(y, ref) < tol
     assert not torch.isnan(y).any()
+    # bit-reproducible run to run (stream-K orders the two partial sums of a shared tile)
+    for _ in range(3):
+        x2, y2 = run()
+        assert torch.equal(x2, x) and torch.equal(y2, y)
 
 
 def test_gemm_linearity_at_full_size(cuda_dev):

@@ -12,7 +12,6 @@
 namespace thmr {
 
 inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool build, int* status, cudaStream_t stream) {
-  (void)stream;
   const thmr_config& c = e->cfg;
   const thmr_weights& w = e->w;
   *status = THMR_OK;
@@ -38,6 +37,8 @@ inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool b
     for (size_t v : cand) sa_elems = v > sa_elems ? v : sa_elems;
   }
   __half* sA = bp.take<__half>(sa_elems);
+  const size_t n_skf = gemm_sk_flag_count(M, HID);
+  unsigned* skf = bp.take<unsigned>(n_skf);        // stream-K ordering flags (zero between launches)
   float* a0 = bp.take<float>(static_cast<size_t>(M) * KP);
   float* x = bp.take<float>(static_cast<size_t>(M) * D);
   float* xn = bp.take<float>(static_cast<size_t>(M) * D);
@@ -115,6 +116,7 @@ inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool b
     d.alpha = kStrictAlpha;
     if (a.taps > 1) { d.taps = a.taps; d.cin = 3 * a.K; d.tap_row0 = -a.dil; d.tap_stride = a.dil; }
     d.seq_pitch = a.seq_pitch; d.seq_lo = a.seq_lo; d.seq_hi = a.seq_hi;
+    if (gemm_sk_flag_count(a.rows, a.N) <= n_skf) d.sk_flags = skf;
     GemmPlan plan;
     const int s = gemm_make_plan(d, &plan);
     if (s != THMR_OK) { err = s; return; }
@@ -353,6 +355,8 @@ inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool b
   }
   e->launches = launches;
   *status = err;
+  if (err == THMR_OK && cudaMemsetAsync(skf, 0, n_skf * sizeof(unsigned), stream) != cudaSuccess)
+    *status = fail(THMR_ERR_CUDA, "cudaMemsetAsync(stream-K flags) failed");
   return total;
 }
 

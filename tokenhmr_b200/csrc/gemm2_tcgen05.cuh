@@ -25,7 +25,69 @@ constexpr uint32_t kG2BBytes = (kG2BN / 2) * kGemmBK * 2;    // 16 KB: this CTA'
 constexpr uint32_t kG2StageBytes = kG2ABytes + kG2BBytes;
 constexpr uint32_t kG2StagingOffset = kG2Stages * kG2StageBytes;
 constexpr uint32_t kG2BarOffset = kG2StagingOffset + kGemmEpiWarps * 4096;
-constexpr uint32_t kG2SmemTotal = kG2BarOffset + 256 + 1024;
+constexpr uint32_t kG2BiasOffset = kG2BarOffset + 256;       // [2 column halves][128] fp32 bias of the current tile
+constexpr uint32_t kG2SmemTotal = kG2BiasOffset + 1024 + 1024;
+static_assert(kG2SmemTotal <= 232448, "CTA-pair GEMM shared memory exceeds 227 KB");
+
+// Work decomposition shared by the three warp roles of a cluster (all of them walk the same item sequence).
+//   classic : tiles (x ksplit) round-robin over the clusters, column tile fastest (clusters running side by side share
+//             A row blocks and weight column blocks in L2).
+//   stream-K: whole tiles quantise badly when tiles / clusters is small -- proj / fc2 have 240 tiles on 74 clusters, i.e.
+//             3.24 waves rounded up to 4.  Hybrid schedule: the first floor(tiles / clusters) - 1 rounds run classic
+//             (148 tiles); the k-blocks of the remaining tiles (92 tiles = 1.24 per cluster) are cut into one contiguous
+//             range per cluster, so every cluster does the same amount of tensor work.  A range boundary inside a tile
+//             splits it between cluster c (head k-blocks, at the END of its range) and cluster c+1 (tail k-blocks, at the
+//             START of its range); both partial sums go into the output through the reduce-add epilogue, the head part
+//             strictly after the tail part (GemmParams::sk_flags), so the result does not depend on timing.  Ranges
+//             are at least one tile long, hence at most two clusters per tile.
+//             (Cutting ALL k-blocks into per-cluster ranges was measured first: the clusters then walk 74 different A row
+//             blocks at any time, A is re-read from HBM once per column tile, fc2 159 us vs 139 us classic.)
+struct G2Work {
+  int tiles_m, tiles_n, num_kb;
+  int tile, dp_tiles, stride, ksplit, kb_per;    // classic phase: flat (tile, k-split) index, < dp_tiles * ksplit
+  int u, u_end;                                  // stream-K phase: units (k-blocks) of tiles [dp_tiles, tiles) of this cluster
+  int cur_tile, cur_m, cur_n, cur_kb0, cur_kb1;  // the current item
+  __device__ void load() {
+    if (tile < dp_tiles * ksplit) {
+      cur_tile = tile / ksplit;
+      const int ks = tile - cur_tile * ksplit;
+      cur_kb0 = ks * kb_per;
+      cur_kb1 = (cur_kb0 + kb_per < num_kb) ? cur_kb0 + kb_per : num_kb;
+    } else {
+      const int t = u / num_kb;
+      cur_tile = dp_tiles + t;
+      cur_kb0 = u - t * num_kb;
+      const int rest = u_end - t * num_kb;
+      cur_kb1 = rest < num_kb ? rest : num_kb;
+    }
+    cur_m = cur_tile / tiles_n;
+    cur_n = cur_tile - cur_m * tiles_n;
+  }
+  // sk_tiles = number of trailing tiles scheduled stream-K (0 = all classic); the host guarantees sk_tiles >= nclusters
+  // and sk_tiles * num_kb * nclusters < 2^31
+  __device__ G2Work(int sk_tiles, int tm, int tn, int nkb, int ks, int cluster, int nclusters)
+      : tiles_m(tm), tiles_n(tn), num_kb(nkb), tile(cluster), dp_tiles(tm * tn - sk_tiles), stride(nclusters), ksplit(ks),
+        kb_per((nkb + ks - 1) / ks), u(0), u_end(0) {
+    if (sk_tiles > 0) {
+      const long long total = static_cast<long long>(sk_tiles) * nkb;
+      u = static_cast<int>(total * cluster / nclusters);
+      u_end = static_cast<int>(total * (cluster + 1) / nclusters);
+    }
+    load();
+  }
+  __device__ bool valid() const { return tile < dp_tiles * ksplit || u < u_end; }
+  __device__ void next() {
+    if (tile < dp_tiles * ksplit) tile += stride;
+    else u = (cur_tile - dp_tiles) * num_kb + cur_kb1;
+    load();
+  }
+  __device__ bool in_streamk() const { return tile >= dp_tiles * ksplit; }
+  __device__ int tile_index() const { return cur_tile; }
+  __device__ int m_blk() const { return cur_m; }
+  __device__ int n_blk() const { return cur_n; }
+  __device__ int kb0() const { return cur_kb0; }
+  __device__ int kb1() const { return cur_kb1; }
+};
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -49,8 +111,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int tiles_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
   const int tiles_n = (p.N + kG2BN - 1) / kG2BN;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
-  const int kb_per = (num_kb + ksplit - 1) / ksplit;
-  const int num_tiles = tiles_m * tiles_n * ksplit;
+  const int sk_tiles = (EPI == kEpiAdd32 && p.sk_flags != nullptr) ? p.sk_tiles : 0;
 
   pdl_launch_dependents();
   if (warp == kWarpTma && lane == 0) {
@@ -87,13 +148,17 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int ks = tile % ksplit;
-        const int rest = tile / ksplit;
-        const int m0 = (rest / tiles_n) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
-        const int n0 = (rest % tiles_n) * kG2BN + static_cast<int>(rank) * (kG2BN / 2);
-        const int kb0 = ks * kb_per;
-        const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+      for (G2Work w(sk_tiles, tiles_m, tiles_n, num_kb, ksplit, cluster_id, num_clusters); w.valid(); w.next()) {
+        const int m0 = w.m_blk() * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+        const int n0 = w.n_blk() * kG2BN + static_cast<int>(rank) * (kG2BN / 2);
+        const int kb0 = w.kb0();
+        const int kb1 = w.kb1();
+        if (EPI == kEpiAdd32 && (p.dbg & 512)) {
+          // experiment (off by default): L2-prefetch this CTA's 128 x 256 fp32 reduce-add target a main loop ahead.
+          // Measured in the step: 18.18 vs 18.01 ms without -- the extra HBM reads arrive while the operands stream.
+#pragma unroll
+          for (int c = 0; c < kG2BN / 32; ++c) tma_prefetch_2d(&tmC, w.n_blk() * kG2BN + c * 32, m0);
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const long long t0 = clock64();
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -131,10 +196,9 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
       bool ready = false;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int ks = tile % ksplit;
-        const int kb0 = ks * kb_per;
-        const int kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+      for (G2Work w(sk_tiles, tiles_m, tiles_n, num_kb, ksplit, cluster_id, num_clusters); w.valid(); w.next()) {
+        const int kb0 = w.kb0();
+        const int kb1 = w.kb1();
         long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         w_tempty += clock64() - t0;
@@ -187,21 +251,37 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // 4 (fp16) / 8 (fp32) TMA operations per tile and CTA instead of 16 / 32.  THMR_GEMM_DBG bit 7 = per-warp stores.
     const bool slab = !(p.dbg & 128);
     uint8_t* slab_buf = smem + kG2StagingOffset + half * 4 * 4096;
+    // Bias of the tile's column half in shared memory (slab mode): each of the half's four warps writes the same 128
+    // values and reads them back as broadcast 16-byte loads -- one LDS per 4 columns instead of 4 shuffles.  The named
+    // barriers of the slab stores keep the four warps inside the same tile, so one buffer per half is enough: nobody
+    // reads the previous tile's bias after the last chunk's barrier.
+    float* sbias = reinterpret_cast<float*>(smem + kG2BiasOffset) + half * 128;
+    const bool packed = slab && !(p.dbg & 256);     // THMR_GEMM_DBG bit 8: the scalar / shuffle epilogue (A/B)
     const uint32_t srow = smem_u32(stage_buf) + lane * 128;
     const int sw = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int ks = tile % ksplit;
-      const int rest = tile / ksplit;
-      const int m0 = (rest / tiles_n) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
-      const int n0 = (rest % tiles_n) * kG2BN;
-      const bool add_bias = p.bias && ks == 0;
+    for (G2Work w(sk_tiles, tiles_m, tiles_n, num_kb, ksplit, cluster_id, num_clusters); w.valid(); w.next()) {
+      const int m0 = w.m_blk() * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+      const int n0 = w.n_blk() * kG2BN;
+      const bool add_bias = p.bias && w.kb0() == 0;
+      // stream-K ordering of a tile shared by two clusters: the tail part (kb0 > 0) lands first and raises the flag,
+      // the head part (kb1 < num_kb) waits for it, then clears it for the next launch.  One flag per store-issuing
+      // thread (cta rank x column half): each covers exactly the output block that thread reduce-adds.
+      const bool sk_item = w.in_streamk();
+      const bool sk_head = sk_item && w.kb1() < num_kb;
+      const bool sk_tail = sk_item && w.kb0() > 0;
+      unsigned int* sk_flag = sk_item ? p.sk_flags + (static_cast<size_t>(w.tile_index()) * 2 + rank) * 2 + half : nullptr;
+      bool sk_waited = false;
       // this warp's 128 bias values (lane l: columns 4l..4l+3 of its column half), fetched while the MMAs run
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
       {
         const int bc = n0 + half * (kG2BN / 2) + lane * 4;
         if (add_bias && lane * 4 < kG2BN / 2 && bc < p.N) bq = __ldg(reinterpret_cast<const float4*>(p.bias + bc));
+      }
+      if (packed) {
+        *reinterpret_cast<float4*>(sbias + lane * 4) = bq;
+        __syncwarp();
       }
       if (lane == 0) mbar_wait(&tfull_bar[acc], acc_phase);   // one polling lane per warp
       __syncwarp();
@@ -212,6 +292,40 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int col0 = n0 + c * kChunkCols;
         uint32_t pk[32];
         if constexpr (EPI == kEpiStore16) {
+          if (packed) {
+            // packed fp32 path: bias add, GELU and the fp16 conversion two columns at a time
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[32];
+              tmem_ld_x32(tmem_base + lane_addr + acc * kG2BN + c * 64 + hh * 32, v);
+              tmem_ld_wait();
+              uint64_t f2[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbias + cc * 64 + hh * 32 + j);   // broadcast
+                f2[j >> 1] = f2_add(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), f2_pack(b4.x, b4.y));
+                f2[(j >> 1) + 1] = f2_add(f2_pack(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), f2_pack(b4.z, b4.w));
+              }
+              if (p.act == kActGelu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f2[j] = gelu_erf2(f2[j]);
+              } else if (p.act == kActRelu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a, b;
+                  f2_unpack(f2[j], a, b);
+                  f2[j] = f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a, b;
+                f2_unpack(f2[j], a, b);
+                __half2 h2 = __floats2half2_rn(a, b);
+                pk[hh * 16 + j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            }
+          } else
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[32];
@@ -277,7 +391,17 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (q == 0 && lane == 0 && col0 < p.N && m0 < p.M && !(p.dbg & 2)) {
             if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, slab_buf, col0, m0);
             else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, slab_buf, col0, m0);
-            else tma_reduce_add_2d(&tmC, slab_buf, col0, m0);
+            else {
+              if (sk_head && !sk_waited) {
+                uint32_t it = 0;
+                while (ld_acquire_gpu(sk_flag) == 0u && ++it < kSpinLimit) {}
+                if (it >= kSpinLimit) atomicExch(&g_pipeline_timeout, 1u);
+                *sk_flag = 0u;                      // consumed: ready for the next launch
+                fence_proxy_async_all();
+                sk_waited = true;
+              }
+              tma_reduce_add_2d(&tmC, slab_buf, col0, m0);
+            }
             tma_store_commit();
           }
         } else {
@@ -294,6 +418,13 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // accumulator buffer free (leader's barrier)
       if ((acc ^= 1) == 0) acc_phase ^= 1;
+      if (sk_tail && slab && q == 0 && lane == 0) {
+        // every reduce-add of this partial tile has been performed in L2: let the head part go
+        tma_store_wait<0>();
+        fence_proxy_async_all();
+        __threadfence();
+        st_release_gpu(sk_flag, 1u);
+      }
     }
     if (lane == 0) tma_store_wait<0>();
   }

@@ -37,7 +37,35 @@ struct GemmDesc {
   int force_bn = 0;
   int force_epi = -1;  // 0 forces the generic epilogue (tests)
   int force_2cta = -1; // -1 auto, 0 never, 1 always (when eligible)
+  unsigned int* sk_flags = nullptr;  // >= gemm_sk_flag_count(M, N) zeroed uints: enables stream-K for reduce-add GEMMs
 };
+
+// Flags a stream-K GEMM of this shape needs (4 per 256 x 256 tile); the buffer must be zero before the first launch and
+// is left zero by every launch, so consecutive GEMMs of one stream can share it.
+inline size_t gemm_sk_flag_count(long long M, long long N) {
+  return static_cast<size_t>((M + 255) / 256) * ((N + kG2BN - 1) / kG2BN) * 4;
+}
+
+// Ordering flags for stream-K GEMMs launched through the stand-alone C entry points (the engine carves its own out of
+// the caller's workspace): one lazily grown, zero-initialised buffer per device.  Launches that use it must be
+// stream-ordered with respect to each other (single-stream use of thmr_gemm_f16, as in the tests).
+inline unsigned int* default_sk_flags(size_t count) {
+  static unsigned int* buf[16] = {nullptr};
+  static size_t cap[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (count > cap[dev]) {
+    unsigned int* nb = nullptr;
+    const size_t n = count < 4096 ? 4096 : count;
+    if (cudaMalloc(&nb, n * sizeof(unsigned int)) != cudaSuccess || cudaMemset(nb, 0, n * sizeof(unsigned int)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;      // (e.g. called under stream capture): the GEMM falls back to whole tiles
+    }
+    buf[dev] = nb;         // the old buffer may still be referenced by earlier plans: intentionally not freed
+    cap[dev] = n;
+  }
+  return buf[dev];
+}
 
 // Which epilogue can serve this GEMM (see gemm_tcgen05.cuh).
 inline int pick_epi(const GemmDesc& d) {
@@ -183,6 +211,24 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
     }
     const long t = tiles * plan->ksplit;
     plan->grid = 2 * static_cast<int>(t < clusters ? t : clusters);
+    // Stream-K (gemm2_tcgen05.cuh) when whole tiles quantise badly over the clusters: needs the reduce-add epilogue,
+    // caller-provided ordering flags, at least two tiles of work per cluster (a tile is then shared by at most two
+    // clusters) and the slab stores (their issuing threads own the flags).  THMR_GEMM_STREAMK=0 disables it.
+    static const int env_sk = [] { const char* e = getenv("THMR_GEMM_STREAMK"); return e ? atoi(e) : 1; }();
+    p.sk_flags = nullptr;
+    p.sk_tiles = 0;
+    // Short tiles do not pay: every partial tile costs a full 128 x 256 fp32 epilogue, which a 10-k-block main loop no
+    // longer hides (proj, 20 k-blocks per tile: 45.3 us with stream-K vs 42.5 us without; fc2, 80: 126.7 vs 138.8 us).
+    if (epi == kEpiAdd32 && d.sk_flags && env_sk && plan->ksplit == 1 && !(p.dbg & 128) && tiles >= 2L * clusters &&
+        tiles % clusters != 0 && num_kb >= 40) {
+      const double eff = static_cast<double>(tiles) / (((tiles + clusters - 1) / clusters) * clusters);
+      const long sk_tiles = tiles % clusters + clusters;      // the last partial round plus one full round
+      if (eff < 0.97 && static_cast<double>(sk_tiles) * num_kb * clusters < 2.0e9) {
+        p.sk_flags = d.sk_flags;
+        p.sk_tiles = static_cast<int>(sk_tiles);
+        plan->grid = 2 * clusters;
+      }
+    }
     return THMR_OK;
   }
   const long tiles_m = (d.M + kGemmBM - 1) / kGemmBM;

@@ -50,6 +50,11 @@ struct GemmParams {
   long long* argmin_out;   // [M] int64 (nullable = normal GEMM)
   const float* row_sq;     // [M]
   const float* col_sq;     // [N]
+  // stream-K (CTA-pair kernel, reduce-add epilogue): non-null = the k-blocks of all tiles are cut into one contiguous
+  // range per cluster; a tile shared by two clusters is reduce-added in a FIXED order through these flags
+  // ([tile][cta rank][column half], zero between launches)
+  unsigned int* sk_flags;
+  int sk_tiles;   // trailing tiles scheduled stream-K (gemm2_tcgen05.cuh G2Work)
   unsigned long long* dbg_counters;  // optional [gridDim.x][8] cycle counters (scripts/dev_gemm_qkv.py)
   int dbg;                 // THMR_GEMM_DBG experiments: 1 = skip epilogue work, 2 = skip only the TMA store
 };
@@ -115,6 +120,54 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));   // 1 ulp-class MUFU reciprocal (p >= 1; p = inf -> 0)
   const float e = 1.0f - r;                       // erf(|x| / sqrt(2))
   return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) e)
+}
+
+// Two GELUs per instruction stream on the packed fp32 pipe (FFMA2: fma.rn.f32x2, IEEE per lane).  Same polynomial as
+// gelu_erf, rearranged so that everything but |x|, max and the reciprocal is packed:
+//   t = -0.5|x|,  a = |x|/sqrt(2) = t * (-sqrt(2)),  r = 1 / (1 + c1 a + ... + c6 a^6)^16,  gelu = max(x, 0) + t * r
+// 18 issue slots per PAIR instead of ~17 per element: the fc1 epilogue (63 M GELUs per layer) is issue-bound.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_splat(float c) { return f2_pack(c, c); }
+// x = (x0, x1) packed -> (gelu(x0), gelu(x1)) packed
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const uint64_t t = f2_pack(fabsf(x0) * -0.5f, fabsf(x1) * -0.5f);
+  const uint64_t a = f2_mul(t, f2_splat(-1.41421356237309505f));
+  uint64_t p = f2_fma(f2_splat(0.0000430638f), a, f2_splat(0.0002765672f));
+  p = f2_fma(p, a, f2_splat(0.0001520143f));
+  p = f2_fma(p, a, f2_splat(0.0092705272f));
+  p = f2_fma(p, a, f2_splat(0.0422820123f));
+  p = f2_fma(p, a, f2_splat(0.0705230784f));
+  p = f2_fma(p, a, f2_splat(1.0f));
+  p = f2_mul(p, p); p = f2_mul(p, p); p = f2_mul(p, p); p = f2_mul(p, p);
+  float p0, p1, r0, r1;
+  f2_unpack(p, p0, p1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+  return f2_fma(t, f2_pack(r0, r1), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
 }
 
 __device__ __forceinline__ void named_bar_sync_64(int id) {

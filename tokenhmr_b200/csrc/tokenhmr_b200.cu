@@ -72,6 +72,7 @@ int thmr_gemm_f16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   d.bias = bias; d.resid = resid; d.ldr = ldr; d.act = act;
   d.out32 = out32; d.ld32 = ld32; d.out16 = static_cast<__half*>(out16); d.ld16 = ld16;
   d.force_bn = block_n;
+  if (resid && resid == out32) d.sk_flags = default_sk_flags(gemm_sk_flag_count(M, N));
   GemmPlan plan;
   THMR_TRY(gemm_make_plan(d, &plan));
   return gemm_launch(plan, static_cast<cudaStream_t>(stream));
