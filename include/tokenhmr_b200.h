@@ -185,7 +185,9 @@ int thmr_smpl_forward(const thmr_smpl* m, const float* rotmats /* [B,24,3,3] */,
  * [tokenization/models/vanilla_pose_vqvae.py:304-346 -> PoseSPEncoderV1 :42-111, quantize_cnn.py:74-86]
  * ---------------------------------------------------------------------------------------------- */
 typedef struct thmr_tok_encoder thmr_tok_encoder;
-typedef struct thmr_tok_conv { const void* w; const float* b; } thmr_tok_conv;  /* f16 [Cout, taps*Cin] tap-major, fp32 bias */
+/* f16 [Cout, taps*3*Cin] tap-major, per tap [hi | hi | lo] of w * 2^8 (split precision: the encoder's output is an
+ * index and is computed at fp32 grade; packed by tokenhmr_b200/tokenizer.py); fp32 bias */
+typedef struct thmr_tok_conv { const void* w; const float* b; } thmr_tok_conv;
 typedef struct thmr_tok_encoder_desc {
   int joints, in_dim;              /* 21, 6 */
   int width, depth, dilation_rate; /* ARCH.WIDTH 512, DEPTH 2, DILATION_RATE 3 */

@@ -12,9 +12,12 @@ pytestmark = pytest.mark.gpu
 # accumulation (DESIGN.md numeric contract); against the oracle emulating exactly that contract only
 # summation order, exp2/erf approximations and rare fp16 rounding flips differ; against the pure-fp32 reference
 # the operand rounding itself shows (measured 2e-4 on vertices at depth 32).
-TOL_EMU = {"_vit_tokens": 1e-3, "_token_out": 1.5e-3, "_pred_body_pose_6d": 1.5e-3, "pred_cam": 1e-3, "pred_cam_t": 1e-3,
-           "pred_keypoints_3d": 1e-3, "pred_vertices": 1e-3, "pred_keypoints_2d": 1.5e-3, "cls_logits_softmax": 2e-2}
-TOL_F32 = {k: 3 * v for k, v in TOL_EMU.items()}
+# Measured on B200 (round 2, depth-2 model, B = 1/2/5): <= 2.7e-4 on every continuous output against either oracle and
+# 4.0e-3 .. 5.3e-3 on cls_logits_softmax (the synthetic class_pred_layer is scaled x20 to make the softmax peaky, which
+# amplifies logit noise twenty-fold; strict mode: 5.7e-5, tests/test_gpu_strict.py).  Tolerances = ~2x the measurement.
+TOL_EMU = {"_vit_tokens": 5e-4, "_token_out": 6e-4, "_pred_body_pose_6d": 6e-4, "pred_cam": 3e-4, "pred_cam_t": 3e-4,
+           "pred_keypoints_3d": 6e-4, "pred_vertices": 6e-4, "pred_keypoints_2d": 8e-4, "cls_logits_softmax": 1e-2}
+TOL_F32 = {k: (2 * v if k != "cls_logits_softmax" else v) for k, v in TOL_EMU.items()}
 KEYS = list(TOL_EMU)
 
 
@@ -44,6 +47,8 @@ def test_tiny_forward_vs_oracle(tiny, B):
     with torch.no_grad():
         emu = O.forward(sd, smpl, img, cfg, emulate_fp16=True, return_intermediates=True)
         f32 = O.forward(sd, smpl, img, cfg, emulate_fp16=False, return_intermediates=True)
+    print(f"tiny B={B} vs emu", {k: f"{rel_err(out[k], emu[k]):.1e}" for k in KEYS})
+    print(f"tiny B={B} vs f32", {k: f"{rel_err(out[k], f32[k]):.1e}" for k in KEYS})
     for k in KEYS:
         assert rel_err(out[k], emu[k]) < TOL_EMU[k], (k, rel_err(out[k], emu[k]))
         assert rel_err(out[k], f32[k]) < TOL_F32[k], (k, rel_err(out[k], f32[k]))

@@ -60,10 +60,28 @@ def test_encoder_state_dict_shares_the_codebook_with_the_forward_weights():
     assert torch.equal(a["tokenizer.quantizer.codebook"], m.sd["tokenizer.quantizer.codebook"])
 
 
+# The encoder runs in split precision (fp32-grade): its indices must EQUAL the fp32 reference's.  The only admissible
+# differences are queries whose two nearest codes are closer than the fp32 evaluation noise of the distance itself
+# (d = |x|^2 - 2 x.c + |c|^2 cancels ~3 digits: with |x|^2 ~ 1e2..1e3 the fp32 noise of d is ~1e-4): gated per element.
+TIE_GAP = 2e-3
+MAX_TIE_FRAC = 0.005
+
+
+def _assert_indices_exact(idx_gpu, ref_idx, gap, what):
+    diff = idx_gpu.cpu() != ref_idx
+    frac = diff.float().mean().item()
+    worst = gap[diff].max().item() if diff.any() else 0.0
+    print(f"{what}: {int(diff.sum())} of {diff.numel()} indices differ, largest reference top-2 gap among them {worst:.2e}")
+    assert (gap[diff] < TIE_GAP).all(), (what, gap[diff])
+    assert frac <= MAX_TIE_FRAC, (what, frac)
+
+
 @pytest.mark.gpu
 def test_gpu_encode_matches_reference_golden(cuda_dev, golden_dir):
     from tokenhmr_b200.tokenizer import EncodeTokens
     g, cfg, sd, sd2, x = _golden(golden_dir)
+    with torch.no_grad():
+        _, lat32 = O.tokenizer_encode(sd, x, cfg, O.Numerics(False))       # == the live reference (pinned above)
     for s, key in ((sd, "idx_synth"), (sd2, "idx_latent_cb")):
         enc = EncodeTokens(cfg, s, device=cuda_dev)
         idx, lat = enc(x, return_latent=True)
@@ -71,40 +89,37 @@ def test_gpu_encode_matches_reference_golden(cuda_dev, golden_dir):
         assert idx.shape == (x.shape[0] * 160,) and idx.dtype == torch.int64 and enc.num_tokens == 160
         ref_lat = torch.from_numpy(g["latent_sub"])
         err = (lat.cpu()[::7] - ref_lat).abs().max().item() / ref_lat.abs().max().item()
-        assert err < 3e-3, err                             # fp16 operands through 9 conv layers vs the fp32 reference
-        same = (idx.cpu().numpy() == g[key]).mean()
-        # indices can only differ where the fp32 reference's own best / second-best gap is within the latent error
-        assert same > 0.97, (key, same)
+        assert err < 2e-5, err                             # fp32-grade through 9 conv layers
+        gap = O.vq_top2_gap(lat32, s["tokenizer.quantizer.codebook"])
+        _assert_indices_exact(idx, torch.from_numpy(g[key].astype(np.int64)), gap, key)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B", [1, 7, 64])
-def test_gpu_encode_vs_contract_oracle(cuda_dev, B):
+@pytest.mark.parametrize("B", [1, 7, 64, 300])
+def test_gpu_encode_vs_fp32_oracle(cuda_dev, B):
     from tokenhmr_b200.tokenizer import EncodeTokens
     cfg = release_config()
     sd = synth.make_tokenizer_encoder_state_dict(cfg, 5)
     x = torch.randn(B, cfg.tok_joints, 6, generator=torch.Generator().manual_seed(B))
     with torch.no_grad():
-        idx16, lat16 = O.tokenizer_encode(sd, x, cfg, O.Numerics(True))     # the engine's numeric contract on the CPU
+        _, lat32 = O.tokenizer_encode(sd, x, cfg, O.Numerics(False))
     # spread the indices: codebook from the latents themselves (+ noise), as in the golden
     gsel = torch.Generator().manual_seed(1)
-    rows = lat16[torch.randint(0, lat16.shape[0], (cfg.nb_code,), generator=gsel)]
+    rows = lat32[torch.randint(0, lat32.shape[0], (cfg.nb_code,), generator=gsel)]
     sd["tokenizer.quantizer.codebook"] = rows + 0.05 * torch.randn(cfg.nb_code, cfg.code_dim, generator=gsel)
-    ref_idx = O.vq_quantize(lat16, sd["tokenizer.quantizer.codebook"])
-    gap = O.vq_top2_gap(lat16, sd["tokenizer.quantizer.codebook"])
+    ref_idx = O.vq_quantize(lat32, sd["tokenizer.quantizer.codebook"])
+    gap = O.vq_top2_gap(lat32, sd["tokenizer.quantizer.codebook"])
     enc = EncodeTokens(cfg, sd, device=cuda_dev)
     idx, lat = enc(x.to(cuda_dev), return_latent=True)
     torch.cuda.synchronize()
-    err = (lat.cpu() - lat16).abs().max().item()
-    assert err < 2e-3 * lat16.abs().max().item(), err     # same operand rounding; only summation order differs
-    diff = idx.cpu() != ref_idx
-    # every disagreement must sit on a near-tie of the reference distances (|d1 - d2| below the latent noise)
-    assert (gap[diff] < 0.5).all(), gap[diff]
-    # (the latent-derived codebook holds ~13 noisy copies of every query for B = 1: near-ties are the common case)
-    assert diff.float().mean().item() < 0.06
-    # a second call reuses the workspace and is bit-identical
+    err = (lat.cpu() - lat32).abs().max().item() / lat32.abs().max().item()
+    assert err < 2e-5, err
+    _assert_indices_exact(idx, ref_idx, gap, f"B={B}")
+    # a second call reuses the workspace and is bit-identical; B = 300 spans two kEncChunk passes
     idx_b = enc(x.to(cuda_dev))
     assert torch.equal(idx, idx_b)
+    if B > 1:                                        # batch independence: the first pose alone gives the same tokens
+        assert torch.equal(enc(x[:1].to(cuda_dev)), idx[:160])
 
 
 @pytest.mark.gpu

@@ -5,8 +5,9 @@
     code_idx = enc(pose6d)                   #      or the flat 'tokenizer.'-prefixed naming used in this repo
                                              # pose6d (B,21,6) CUDA/CPU fp32 -> (B*160,) int64 on the GPU
 
-All arithmetic runs in libtokenhmr_b200.so (`thmr_tok_encode`): implicit-GEMM Conv1d layers on the tcgen05 kernel and
-the split-precision distance GEMM with the arg-min in its epilogue.  Python repacks the weights once and allocates
+All arithmetic runs in libtokenhmr_b200.so (`thmr_tok_encode`) in split precision (fp32-grade: the output is an index and
+has to equal the fp32 reference's): implicit-GEMM Conv1d layers on the tcgen05 kernel over split-fp16 operands and the
+split-precision distance GEMM with the arg-min in its epilogue.  Python repacks the weights once and allocates
 tensors; there is no CPU path.
 """
 from __future__ import annotations
@@ -20,6 +21,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, lib
 from .config import TokenHMRConfig
+from .weights import split_weight
 
 _CIN0 = 64   # kEncCin0 in csrc/tok_encoder.cuh
 
@@ -37,14 +39,17 @@ class EncodeTokens(nn.Module):
         self._keep: List[torch.Tensor] = []
         dev = self.device
 
-        def conv(prefix: str, pad_cin: Optional[int] = None) -> _lib.TokConv:
+        def conv(prefix: str, pad_cin: Optional[int] = None, gathered: bool = False) -> _lib.TokConv:
             w = net[prefix + ".weight"].detach().float()                   # [Cout, Cin, k]
             cout, cin, k = w.shape
             if pad_cin is not None:
                 wp = torch.zeros(cout, pad_cin, k)
                 wp[:, :cin] = w
                 w, cin = wp, pad_cin
-            wt = w.permute(0, 2, 1).reshape(cout, k * cin).to(dev, torch.float16).contiguous()   # tap-major
+            # tap-major, split precision (csrc/strict.cuh): per tap [hi | hi | lo] of w * 2^8; the stride-2 conv's four
+            # taps are gathered into ONE operand row on the device, so its weight is split as a single 4*cin-wide tap
+            wt = w.permute(0, 2, 1).reshape(cout, k * cin).to(dev)
+            wt = split_weight(wt, taps=(1 if gathered else k))
             b = net[prefix + ".bias"].detach().to(dev, torch.float32).contiguous()
             self._keep += [wt, b]
             return _lib.TokConv(wt.data_ptr(), b.data_ptr())
@@ -60,7 +65,7 @@ class EncodeTokens(nn.Module):
         for u in range(1, cfg.tok_size_mul):
             d.conv_up[u] = conv(f"{e}.{idx + 1}")
             idx += 3
-        d.conv_down = conv(f"{e}.{idx}.0")
+        d.conv_down = conv(f"{e}.{idx}.0", gathered=True)
         for k in range(cfg.tok_depth):
             d.res_conv1[k] = conv(f"{e}.{idx}.1.model.{k}.conv1")
             d.res_conv2[k] = conv(f"{e}.{idx}.1.model.{k}.conv2")

@@ -35,6 +35,23 @@ def strip_checkpoint(state_dict: Dict[str, torch.Tensor], tokenizer_net: Dict[st
 STRICT_W_SCALE = 256.0     # kStrictWScale (csrc/strict.cuh)
 
 
+def split_weight(t: torch.Tensor, taps: int = 1) -> torch.Tensor:
+    """[out, taps*in] -> f16 [out, taps*3*in], per tap [hi | hi | lo] of w * STRICT_W_SCALE (hi = fp16(w * 2^8),
+    lo = fp16(w * 2^8 - hi)): the B operand of the split-precision GEMMs (csrc/strict.cuh)."""
+    t = t.detach().to(dtype=torch.float32)
+    amax = float(t.abs().max()) if t.numel() else 0.0
+    if not amax < 65504.0 / STRICT_W_SCALE:
+        raise _lib.ThmrError(f"split precision: weight magnitude {amax:g} exceeds the split-fp16 range "
+                             f"(|w| < {65504.0 / STRICT_W_SCALE:g})")
+    ws = t * STRICT_W_SCALE
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    out_f, k = t.shape
+    cin = k // taps
+    hi3, lo3 = hi.view(out_f, taps, cin), lo.view(out_f, taps, cin)
+    return torch.cat([hi3, hi3, lo3], dim=2).reshape(out_f, taps * 3 * cin).contiguous()
+
+
 class PackedWeights:
     """Owns the device tensors the engine points into (must outlive the engine)."""
 
@@ -47,24 +64,9 @@ class PackedWeights:
         self._keep: List[torch.Tensor] = []
         g = lambda n: sd[n]
 
-        def split_w(t: torch.Tensor, taps: int = 1) -> torch.Tensor:
-            """[out, taps*in] fp32 -> [out, taps*3*in] fp16, per tap [hi | hi | lo] of w * STRICT_W_SCALE."""
-            t = t.detach().to(device=device, dtype=torch.float32)
-            amax = float(t.abs().max()) if t.numel() else 0.0
-            if not amax < 65504.0 / STRICT_W_SCALE:
-                raise _lib.ThmrError(f"strict mode: weight magnitude {amax:g} exceeds the split-fp16 range "
-                                     f"(|w| < {65504.0 / STRICT_W_SCALE:g})")
-            ws = t * STRICT_W_SCALE
-            hi = ws.to(torch.float16)
-            lo = (ws - hi.to(torch.float32)).to(torch.float16)
-            out_f, k = t.shape
-            cin = k // taps
-            hi3, lo3 = hi.view(out_f, taps, cin), lo.view(out_f, taps, cin)
-            return torch.cat([hi3, hi3, lo3], dim=2).reshape(out_f, taps * 3 * cin).contiguous()
-
         def f16(t: torch.Tensor, taps: int = 1) -> int:
             if self.strict:
-                t = split_w(t, taps)
+                t = split_weight(t.detach().to(device=device), taps)
             else:
                 t = t.detach().to(device=device, dtype=torch.float16).contiguous()
             self._keep.append(t)
