@@ -290,9 +290,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # a wedged collective must never eat the box's time limit: dump every thread's Python stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("THMR_BENCH_WATCHDOG", "900")), exit=True)
     # NCCL_DEBUG is left alone: its log is the evidence for rank count and transport (the JSON line is printed last)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # The process group only carries control traffic (the 128-byte NCCL unique id, shard sizes, barriers, the max over
+        # ranks of the timings): gloo.  The data path is the library's own NCCL communicator (thmr_comm_create).
+        backend = os.environ.get("THMR_BENCH_PG", "gloo")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        else:
+            dist.init_process_group("gloo")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     cfg = release_config()
@@ -305,6 +314,7 @@ def main():
     img_dev = img_host.to(dev)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -312,7 +322,7 @@ def main():
     def max_over_ranks(ms: float) -> float:
         if world == 1:
             return ms
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms], device=dev if dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -444,15 +454,29 @@ def main():
             "clocks": clocks, "roofline": roofline, "attention": attention, "kernel_families": families,
             "strict": strict, "standalone": standalone, "cpu_baseline": cpu,
         })
-    del sharded
+    # Teardown must not be able to lose the measurement: if it does not finish in 30 s, print the line and leave.
+    def bail():
+        if rank == 0:
+            print(line, flush=True)
+        os._exit(0)
+    guard = threading.Timer(30.0, bail)
+    guard.daemon = True
+    guard.start()
     if world > 1:
+        pipe = None
+        sharded.close()              # releases the graphs that captured the communicator, then destroys it
         dist.barrier()
         dist.destroy_process_group()
+    guard.cancel()
+    faulthandler.cancel_dump_traceback_later()
     if rank == 0:
         if world > 1:
             time.sleep(1.0)          # let the other ranks' NCCL teardown messages drain: the JSON line stays last
         sys.stdout.flush()
         print(line, flush=True)
+    if world > 1:
+        sys.stderr.flush()
+        os._exit(0)                  # skip libnccl's atexit chatter (NCCL_DEBUG=INFO): nothing may follow the JSON line
 
 
 if __name__ == "__main__":

@@ -43,7 +43,10 @@ def _worker(rank, world, port, q, global_batch, use_graph):
         # this rank's own rows are bit-identical to what its local forward wrote (in-place: nothing was copied)
         local = model({"img": img[lo:hi]})
         own_equal = torch.equal(g["pred_vertices"][lo:hi], local["pred_vertices"])
-        q.put((rank, None, errs, own_equal, tuple(got["cls_logits_softmax_local"].shape)))
+        lshape = tuple(got["cls_logits_softmax_local"].shape)
+        del got, want, local
+        sharded.close()                           # must return promptly even though CUDA graphs captured the communicator
+        q.put((rank, None, errs, own_equal, lshape))
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
         import traceback

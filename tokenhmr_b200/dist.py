@@ -139,12 +139,23 @@ class ShardedTokenHMR:
             check(lib().thmr_comm_create(ident[0], self.world, self.rank, ctypes.byref(h)))
         self._comm = h
 
+    def close(self) -> None:
+        """Destroy the library's communicator.  CUDA graphs that captured its collectives keep the communicator alive
+        (ncclCommDestroy would wait for them forever), so the engine's sharded buffer sets -- and with them their graphs --
+        are released first."""
+        if self._comm:
+            from ._lib import lib
+            m = self.model
+            for key in [k for k, st in m._bufs.items() if st.get("shard") is not None]:
+                st = m._bufs.pop(key)
+                st["graph"] = None
+            torch.cuda.synchronize(m.device)
+            comm, self._comm = self._comm, None
+            lib().thmr_comm_destroy(comm)
+
     def __del__(self):
         try:
-            if self._comm:
-                from ._lib import lib
-                lib().thmr_comm_destroy(self._comm)
-                self._comm = None
+            self.close()
         except Exception:
             pass
 
