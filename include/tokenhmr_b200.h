@@ -324,6 +324,15 @@ int thmr_engine_num_steps(const thmr_engine* e);
 int thmr_engine_step_info(const thmr_engine* e, int i, const char** name, double* flops, double* bytes);
 int thmr_engine_profile(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
                         void* stream, float* step_ms, int cap);
+/* In-graph timing.  Every kernel of the default-mode forward writes the GPU's global nanosecond timer into its step's
+ * slot when it starts; thmr_engine_forward_stamped = thmr_engine_forward + one trailing 1-warp kernel that stamps the
+ * end.  Capture it in a CUDA graph, replay, then thmr_engine_read_stamps (synchronous D2H): host_ns[i] = start of step i
+ * (0 = that step launched no stamped kernel: its time belongs to the previous step), host_ns[n_steps] = end.  Kernels of a
+ * stream run back to back, so the differences are each step's share of the real replay, with no events in between.
+ * Returns the number of entries (n_steps + 1) or a negative status. */
+int thmr_engine_forward_stamped(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
+                                void* stream);
+int thmr_engine_read_stamps(const thmr_engine* e, unsigned long long* host_ns, int cap);
 /* Backbone only: ViT.forward [vit.py:341-343]: img -> tokens fp32 [B,192,D] (token-major). */
 int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream);
 

@@ -1,4 +1,4 @@
-"""Two-chain attention kernel: timing + per-role cycle counters (THMR_ATTN_GEN=3)."""
+"""Two-chain attention kernel: timing + per-role cycle counters."""
 import os
 import torch
 
@@ -26,7 +26,7 @@ ref = torch.softmax((q * 80 ** -0.5) @ k.transpose(-1, -2), -1) @ v
 ref = ref.transpose(1, 2).reshape(B * 192, H * 80)
 print("max abs err vs fp32 torch:", (out.float() - ref).abs().max().item(), "ref max", ref.abs().max().item())
 run(3, False)
-print(f"attention bs=64 gen={os.environ.get('THMR_ATTN_GEN', '3')} knobs={os.environ.get('THMR_ATTN_TS', '0')}: L2-warm {run(20, False)*1e3:.1f} us, L2-flushed {run(20, True)*1e3:.1f} us per layer")
+print(f"attention bs=64 knobs={os.environ.get('THMR_ATTN_TS', '0')}: L2-warm {run(20, False)*1e3:.1f} us, L2-flushed {run(20, True)*1e3:.1f} us per layer")
 c = cnt.view(148, 32).float().mean(0).tolist()
 print(f"MMA issuer 0: total {c[0]:.0f} wait o_empty {c[1]:.0f} qk_full {c[16]:.0f} p_full {c[17]:.0f} v_full {c[18]:.0f}")
 print(f"MMA issuer 1: total {c[8]:.0f} wait o_empty {c[15]:.0f} qk_full {c[19]:.0f} p_full {c[20]:.0f} v_full {c[21]:.0f}")

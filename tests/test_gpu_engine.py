@@ -126,9 +126,9 @@ def test_batch_independence(tiny):
 
 
 def test_decoder_full_tile_vs_oracle(tiny):
-    """bs = 64 vs bs = 65 (with THMR_DEC_FUSED=1 the first fills the fused decoder kernel's 64-row tile, dec_fused.cuh,
-    and the second takes the one-launch-per-layer path): the decoder output token of the shared images must agree to
-    accumulation noise, and the bs = 64 result must match the CPU oracle of the decoder (engine contract) on a few rows."""
+    """bs = 64 vs bs = 65 (a full 64-row decoder tile vs one row spilling into a second tile): the decoder output token
+    of the shared images must agree to accumulation noise, and the bs = 64 result must match the CPU oracle of the
+    decoder (engine contract) on a few rows."""
     from oracle import tokenhmr_oracle as O
     from tokenhmr_b200 import synth
     cfg, sd, smpl, model = tiny
@@ -194,3 +194,32 @@ def test_release_forward_vs_reference_golden(cuda_dev, golden_dir):
     out = model({"img": synth.make_images(64, cfg, 5)})
     assert all(torch.isfinite(v).all() for v in out.values() if isinstance(v, torch.Tensor))
     torch.testing.assert_close(out["cls_logits_softmax"].sum(-1), torch.ones(64, 160, device=cuda_dev), atol=1e-4, rtol=0)
+
+
+def test_in_graph_stamps_account_for_the_whole_replay(tiny):
+    """profile_in_graph: per-step times from start stamps written inside the CUDA-graph replay.  They are non-negative,
+    cover every launch group that owns a stamped kernel, and sum to the duration of one replay (nothing is inserted
+    between the launches, unlike the event-separated profile())."""
+    from tokenhmr_b200 import synth
+    cfg, _, _, model = tiny
+    img = synth.make_images(4, cfg, seed=2).cuda()
+    rows = model.profile_in_graph(img, replays=3)
+    assert len(rows) == len(model.profile(img))
+    assert all(ms >= 0 for _, ms, _, _ in rows)
+    names = {n for n, ms, _, _ in rows if ms > 0}
+    assert {"vit.layernorm", "vit.qkv_gemm", "vit.attention", "vit.proj_gemm", "vit.fc1_gelu_gemm", "vit.fc2_gemm"} <= names
+    total = sum(ms for _, ms, _, _ in rows)
+    # one replay of the same stamped graph, timed with events around it
+    st = model._state(4, False, slot=-1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st["graph"].replay()
+    e0.record()
+    for _ in range(5):
+        st["graph"].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) / 5
+    assert 0.6 * per < total < 1.4 * per, (total, per)
+    # the stamped forward computes the same outputs as the plain one
+    a = model({"img": img})["pred_vertices"]
+    assert torch.equal(st["t"]["pred_vertices"], a)

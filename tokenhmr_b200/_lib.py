@@ -158,6 +158,8 @@ SIGNATURES = {
     "thmr_engine_profile": (c_int, [c_void_p, c_void_p, c_int, POINTER(Outputs), c_void_p, c_void_p,
                                     POINTER(c_float), c_int]),
     "thmr_engine_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "thmr_engine_forward_stamped": (c_int, [c_void_p, c_void_p, c_int, POINTER(Outputs), c_void_p, c_void_p]),
+    "thmr_engine_read_stamps": (c_int, [c_void_p, POINTER(ctypes.c_uint64), c_int]),
     "thmr_comm_unique_id": (c_int, [c_void_p]),
     "thmr_comm_create": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "thmr_comm_destroy": (None, [c_void_p]),

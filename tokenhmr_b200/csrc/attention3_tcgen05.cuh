@@ -1,8 +1,8 @@
-// Fused ViT attention, third generation: two independent tile chains per CTA.
+// Fused ViT attention (reference: Attention.forward, vit.py:116-122): two independent tile chains per CTA.
 //
-// Generations 1 and 2 run S-MMA -> softmax -> PV-MMA -> epilogue as one serial chain per 128-row tile, with the same
-// eight warps doing every softmax and every epilogue (counters: each role idle ~60 %, ~12 k cycles per head while
-// the tensor pipe needs ~1.9 k and the exp unit ~2.3 k).  Here the CTA holds TWO tile buffers in TMEM, each owned by
+// The first two generations of this kernel (removed) ran S-MMA -> softmax -> PV-MMA -> epilogue as one serial chain per
+// 128-row tile, with the same eight warps doing every softmax and every epilogue (counters: each role idle ~60 %, ~12 k
+// cycles per head while the tensor pipe needs ~1.9 k and the exp unit ~2.3 k).  Here the CTA holds TWO tile buffers in TMEM, each owned by
 // its own group of four softmax warps and its own MMA-issuing thread, so that one group's exponentials overlap the
 // other group's MMAs, TMEM traffic and epilogue.  (One issuer polling both chains was tried first: a non-blocking
 // mbarrier probe costs 130-260 cycles, so every hand-over was detected ~500 cycles late.)
@@ -28,7 +28,7 @@
 #pragma once
 #include <stdlib.h>
 
-#include "attention2_tcgen05.cuh"
+#include "attention_common.cuh"
 
 namespace thmr {
 
@@ -163,6 +163,7 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                      static_cast<int>(gridDim.x);
 
   pdl_launch_dependents();
+  stamp_start(p.stamp);
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmO);
@@ -193,6 +194,9 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     // ---------------------------------------------------------------- TMA producers: lane 0 streams Q,K, lane 1 streams V
     // (two threads so that a V stage still held by the PV MMAs never delays the next Q,K load)
     if (lane < 2) {
+      // bit 4 of the knobs (THMR_L2_HINTS & 2): Q, K, V are dead once this kernel has read them -> evict_first
+      const bool hint = (p.p_in_tmem & 16) != 0;
+      const uint64_t pol = l2_policy_evict_first();
       for (int i = 0; i < nheads; ++i) {
         const int prob = blockIdx.x + i * gridDim.x;
         const int b = prob / p.heads, h = prob % p.heads;
@@ -202,12 +206,18 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         if (lane == 0) {
           mbar_wait(&qk_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&qk_full[st], 2 * kAttMatBytes);
-          tma_load_3d(sQ, &tmQKV, &qk_full[st], 0, b * kAttTokens, h * kAttChunks);
-          tma_load_3d(sQ + kAttMatBytes, &tmQKV, &qk_full[st], 0, b * kAttTokens, (p.heads + h) * kAttChunks);
+          if (hint) {
+            tma_load_3d_hint(sQ, &tmQKV, &qk_full[st], 0, b * kAttTokens, h * kAttChunks, pol);
+            tma_load_3d_hint(sQ + kAttMatBytes, &tmQKV, &qk_full[st], 0, b * kAttTokens, (p.heads + h) * kAttChunks, pol);
+          } else {
+            tma_load_3d(sQ, &tmQKV, &qk_full[st], 0, b * kAttTokens, h * kAttChunks);
+            tma_load_3d(sQ + kAttMatBytes, &tmQKV, &qk_full[st], 0, b * kAttTokens, (p.heads + h) * kAttChunks);
+          }
         } else {
           mbar_wait(&v_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[st], kAttMatBytes);
-          tma_load_3d(sQ + 2 * kAttMatBytes, &tmQKV, &v_full[st], 0, b * kAttTokens, (2 * p.heads + h) * kAttChunks);
+          if (hint) tma_load_3d_hint(sQ + 2 * kAttMatBytes, &tmQKV, &v_full[st], 0, b * kAttTokens, (2 * p.heads + h) * kAttChunks, pol);
+          else tma_load_3d(sQ + 2 * kAttMatBytes, &tmQKV, &v_full[st], 0, b * kAttTokens, (2 * p.heads + h) * kAttChunks);
         }
       }
     }
@@ -415,12 +425,6 @@ inline int attention3_launch(const AttnPlan& plan, cudaStream_t st) {
   }
 }
 
-// THMR_ATTN_GEN selects the kernel generation (3 = two-chain kernel, default; 2 = P-in-TMEM single chain; 1 = first).
-inline int attention_dispatch(const AttnPlan& plan, cudaStream_t st) {
-  static const int gen = [] { const char* e = getenv("THMR_ATTN_GEN"); return e ? atoi(e) : 3; }();
-  if (gen == 1) return attention_launch(plan, st);
-  if (gen == 2) return attention2_launch(plan, st);
-  return attention3_launch(plan, st);
-}
+inline int attention_dispatch(const AttnPlan& plan, cudaStream_t st) { return attention3_launch(plan, st); }
 
 }  // namespace thmr

@@ -110,6 +110,18 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 #ifdef __CUDACC__
+// In-graph timing: the first thread of block 0 of a kernel records the global nanosecond timer at kernel start
+// (nullptr = off).  Kernels of a stream run back to back, so start(next) - start(this) is this kernel's share of the
+// step inside the real CUDA-graph replay, without events between the launches (thmr_engine_forward_stamped).
+__device__ __forceinline__ void stamp_start(unsigned long long* stamp) {
+  if (stamp != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *stamp = t;
+  }
+}
+__global__ void stamp_kernel(unsigned long long* stamp) { stamp_start(stamp); }
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -25,7 +25,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // One thread per (row, c, dy): writes P consecutive fp16 (32 B for P=16).
 // ------------------------------------------------------------------------------------------------
 __global__ void im2col_patch_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int S, int x0,
-                                    int Wc, int P, int pad, int gh, int gw) {
+                                    int Wc, int P, int pad, int gh, int gw, unsigned long long* stamp) {
+  stamp_start(stamp);
   const long total = static_cast<long>(B) * gh * gw * 3 * P;
   const long t = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (t >= total) return;
@@ -58,7 +59,8 @@ template <int VEC4, bool PREFETCH>  // float4 loads per lane; PREFETCH: the next
 __global__ void __launch_bounds__(256, VEC4 > 10 ? (PREFETCH ? 1 : 2) : (PREFETCH ? 2 : 4))
 layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu,
-                     int out_t) {
+                     int out_t, unsigned long long* stamp) {
+  stamp_start(stamp);
   // gamma/beta staged in shared memory once per (persistent) block: read from global inside the output loop they
   // were the largest stall of the kernel (an L2-latency load per 4 outputs, after the reductions)
   extern __shared__ float4 s_gb[];   // [2][C/4]
@@ -156,7 +158,9 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // Wide rows (C up to 64K, e.g. the 10240-wide FCBlock norm): one block per row, three passes over L1/L2.
 __global__ void __launch_bounds__(256)
 layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu) {
+                      __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu,
+                      unsigned long long* stamp) {
+  stamp_start(stamp);
   __shared__ float red[8];
   __shared__ float bcast;
   const int row = blockIdx.x;
@@ -190,7 +194,8 @@ layernorm_wide_kernel(const float* __restrict__ x, const float* __restrict__ gam
 }
 
 inline int layernorm_launch(const float* x, const float* gamma, const float* beta, __half* y16, int ld16, float* y32,
-                            int R, int C, float eps, int relu, int out_t, cudaStream_t st) {
+                            int R, int C, float eps, int relu, int out_t, cudaStream_t st,
+                            unsigned long long* stamp = nullptr) {
   THMR_CHECK(C % 4 == 0, "layernorm: C=%d not a multiple of 4", C);
   if (ld16 == 0) ld16 = C;
   if (C <= 2048) {
@@ -205,9 +210,9 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
 #define THMR_LN_LAUNCH(V)                                                                                           \
   do {                                                                                                             \
     if (prefetch) THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, true>, grid, threads, smem, st, x, gamma, beta, y16, \
-                                       ld16, y32, R, C, eps, relu, out_t));                                        \
+                                       ld16, y32, R, C, eps, relu, out_t, stamp));                                 \
     else THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, false>, grid, threads, smem, st, x, gamma, beta, y16, ld16,   \
-                              y32, R, C, eps, relu, out_t));                                                       \
+                              y32, R, C, eps, relu, out_t, stamp));                                                \
   } while (0)
     if (vec4 <= 1) THMR_LN_LAUNCH(1);
     else if (vec4 <= 8) THMR_LN_LAUNCH(8);
@@ -216,7 +221,7 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
 #undef THMR_LN_LAUNCH
   } else {
     THMR_CHECK(out_t == 0, "layernorm: transposed output needs C <= 2048");
-    layernorm_wide_kernel<<<R, 256, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu);
+    layernorm_wide_kernel<<<R, 256, 0, st>>>(x, gamma, beta, y16, ld16, y32, R, C, eps, relu, stamp);
   }
   THMR_CUDA(cudaGetLastError());
   return THMR_OK;

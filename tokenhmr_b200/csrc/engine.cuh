@@ -8,7 +8,6 @@
 
 #include "attention3_tcgen05.cuh"
 #include "common.cuh"
-#include "dec_fused.cuh"
 #include "elementwise.cuh"
 #include "gemm_host.cuh"
 #include "head_kernels.cuh"
@@ -40,7 +39,7 @@ struct Step {
 };
 
 // ---- SMPL stage (shared by thmr_lbs / thmr_smpl_forward / the engine) -----------------------------------
-// The pose-blend offsets (fp32, 82.7 KB per pose) are produced by a GEMM and consumed by the skinning kernel.
+// The blended vertices v_posed (fp32, 82.7 KB per pose) are produced by a GEMM and consumed by the skinning kernel.
 // Poses are processed in chunks of kSmplChunk so that the offsets of a chunk (42 MB) stay L2-resident between the
 // two kernels instead of making a round trip through HBM.
 constexpr int kSmplChunk = 512;
@@ -88,11 +87,9 @@ inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const 
     if (!blend_plans) THMR_TRY(smpl_blend_plan(m, ws, p0, n, &local));
     THMR_TRY(gemm_launch(*plan, st));
     dim3 grid((m.V + kSkinThreads - 1) / kSkinThreads, (n + kSkinPoses - 1) / kSkinPoses);
-    smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.v_template, m.shapedirs, m.nb, m.w_idx, m.w_val, m.ell,
-                                                    betas + static_cast<size_t>(p0) * m.nb,
-                                                    ws.A + static_cast<size_t>(p0) * kSmplJ * 12, ws.offsets, ws.off_pitch,
-                                                    verts + static_cast<size_t>(p0) * m.V * 3, static_cast<long>(m.V) * 3,
-                                                    m.V, n);
+    smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.w_idx, m.w_val, m.ell, ws.A + static_cast<size_t>(p0) * kSmplJ * 12,
+                                                    ws.offsets, ws.off_pitch, verts + static_cast<size_t>(p0) * m.V * 3,
+                                                    static_cast<long>(m.V) * 3, m.V, n);
     THMR_CUDA(cudaGetLastError());
   }
   if (joints44) {
@@ -119,7 +116,10 @@ struct thmr_engine {
   std::vector<thmr::Step> steps;
   size_t vit_steps = 0;  // steps [0, vit_steps) = backbone
   int launches = 0;      // kernels per forward (strict mode counts them while building; 0 = default-path formula)
+  unsigned long long* stamps = nullptr;   // [kMaxStamps] in the workspace: start stamp of step i, end stamp at [n_steps]
 };
+
+constexpr int kMaxStamps = 2048;
 
 namespace thmr {
 
@@ -153,9 +153,9 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   float* q32 = bp.take<float>(static_cast<size_t>(B) * inner);
   __half* att16 = bp.take<__half>(static_cast<size_t>(B) * inner);
   __half* hid16 = bp.take<__half>(static_cast<size_t>(B) * c.dec_mlp_dim);
-  unsigned* dec_barrier = bp.take<unsigned>(32);   // grid barrier counter of the fused decoder kernel
   const size_t n_skf = gemm_sk_flag_count(M, static_cast<long long>(c.vit_mlp_ratio) * D);
   unsigned* skf = bp.take<unsigned>(n_skf);        // stream-K ordering flags (zero between launches)
+  unsigned long long* stamps = bp.take<unsigned long long>(kMaxStamps);   // in-graph start stamps, one slot per step
   float* readout = bp.take<float>(static_cast<size_t>(B) * 32);
   float* mt32 = bp.take<float>(static_cast<size_t>(B) * TN * CH);
   float* cx = bp.take<float>(static_cast<size_t>(B) * TN * CH);
@@ -203,7 +203,10 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     size_t size() const { return v.size(); }
   } S{e->steps};
   int err = THMR_OK;
-  auto add_gemm = [&](const GemmDesc& d) {
+  e->stamps = stamps;
+  auto slot = [&]() -> unsigned long long* { return S.size() < static_cast<size_t>(kMaxStamps - 1) ? stamps + S.size() : nullptr; };
+  auto add_gemm = [&](GemmDesc d) {
+    d.stamp = slot();
     GemmPlan plan;
     const int s = gemm_make_plan(d, &plan);
     if (s != THMR_OK) { err = s; return; }
@@ -220,14 +223,18 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     d.bias = bias; d.act = act; d.resid = resid; d.ldr = N;
     d.out32 = o32; d.ld32 = N; d.out16 = o16; d.ld16 = N;
     if (gemm_sk_flag_count(rows, N) <= n_skf) d.sk_flags = skf;
+    d.a_dead = (A == xn || A == ao || A == hbuf || (A >= xn && A < xn + static_cast<size_t>(M) * D) ||
+                (A >= ao && A < ao + static_cast<size_t>(M) * D) ||
+                (A >= hbuf && A < hbuf + static_cast<size_t>(M) * c.vit_mlp_ratio * D)) ? 1 : 0;
     add_gemm(d);
   };
   auto ln = [&](const float* in, const float* g, const float* b, __half* o16, float* o32, int R, int C, float eps,
                 int relu, int out_t) {
     S.flops = 0;
     S.bytes = static_cast<double>(R) * C * (4 + (o16 ? 2 : 0) + (o32 ? 4 : 0));
+    unsigned long long* sp = slot();
     S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
-      return layernorm_launch(in, g, b, o16, 0, o32, R, C, eps, relu, out_t, st);
+      return layernorm_launch(in, g, b, o16, 0, o32, R, C, eps, relu, out_t, st, sp);
     });
   };
 
@@ -235,10 +242,11 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   {
     const int S_ = c.image_size, x0 = (c.image_size - c.crop_w) / 2, Wc = c.crop_w, P = c.patch, pad = c.patch_pad;
     S.tag("vit.patch_im2col", 0, static_cast<double>(B) * 3 * c.image_size * c.crop_w * 4 + static_cast<double>(M) * KP * 2);
+    unsigned long long* sp = slot();
     S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
       const long total_t = static_cast<long>(B) * gh * gw * 3 * P;
       im2col_patch_kernel<<<static_cast<unsigned>((total_t + 255) / 256), 256, 0, st>>>(r.img, a0, B, S_, x0, Wc, P, pad,
-                                                                                       gh, gw);
+                                                                                       gh, gw, sp);
       THMR_CUDA(cudaGetLastError());
       return THMR_OK;
     });
@@ -278,6 +286,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
       AttnPlan ap;
       const int s = attention_make_plan(qkvs, 3 * D, bn, H, aos, D, nullptr, &ap);
       if (s != THMR_OK) err = s;
+      ap.p.stamp = slot();
       S.push_back([ap](const RunCtx&, cudaStream_t st) -> int { return attention_dispatch(ap, st); });
     }
     S.tag("vit.proj_gemm");
@@ -294,9 +303,10 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     S.tag("vit.layernorm", 0, static_cast<double>(M) * D * 6);
     const float* g = w.last_g; const float* b = w.last_b;
     const float eps = c.vit_ln_eps;
+    unsigned long long* sp = slot();
     S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
       float* t32 = r.vit_tokens_only ? r.vit_tokens_only : r.out.vit_tokens;
-      return layernorm_launch(x, g, b, feat, 0, t32, M, D, eps, 0, 0, st);
+      return layernorm_launch(x, g, b, feat, 0, t32, M, D, eps, 0, 0, st, sp);
     });
   }
   e->vit_steps = S.size();
@@ -305,31 +315,6 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   S.tag("dec.to_kv_gemm");
   linear(feat, D, M, w.kv_w, L * 2 * inner, D, nullptr, kActNone, nullptr, kv);
   S.tag("dec.token_ops");
-  // THMR_DEC_FUSED=1: one persistent kernel for the 6 decoder layers (dec_fused.cuh) when the batch fits its 64-row
-  // tile.  Measured on B200 (same-box A/B, bs = 64, CUDA graph): 0.65 ms for the fused kernel vs 0.9 ms of eager
-  // launches, but no difference in the graph-replayed step (18.20 vs 18.25 ms), so the well-trodden path of one launch
-  // per LayerNorm / Linear / attention stays the default.
-  static const int env_fused = [] { const char* v = getenv("THMR_DEC_FUSED"); return v ? atoi(v) : 0; }();
-  const bool fused_dec = env_fused && dec_fused_supported(B, E, inner, c.dec_mlp_dim, c.dec_heads, c.dec_dim_head, T, L);
-  if (fused_dec) {
-    DecFusedParams fp;
-    memset(&fp, 0, sizeof(fp));
-    for (int l = 0; l < L; ++l) {
-      const thmr_dec_layer& dw = e->dec[l];
-      DecFusedLayer& f = fp.L[l];
-      f.ln0_g = dw.ln0_g; f.ln0_b = dw.ln0_b; f.sa_v_w = static_cast<const __half*>(dw.sa_v_w);
-      f.sa_out_w = static_cast<const __half*>(dw.sa_out_w); f.sa_out_b = dw.sa_out_b;
-      f.ln1_g = dw.ln1_g; f.ln1_b = dw.ln1_b; f.ca_q_w = static_cast<const __half*>(dw.ca_q_w);
-      f.ca_out_w = static_cast<const __half*>(dw.ca_out_w); f.ca_out_b = dw.ca_out_b;
-      f.ln2_g = dw.ln2_g; f.ln2_b = dw.ln2_b; f.ff1_w = static_cast<const __half*>(dw.ff1_w); f.ff1_b = dw.ff1_b;
-      f.ff2_w = static_cast<const __half*>(dw.ff2_w); f.ff2_b = dw.ff2_b;
-    }
-    fp.depth = L; fp.B = B; fp.E = E; fp.inner = inner; fp.mlp = c.dec_mlp_dim; fp.heads = c.dec_heads; fp.T = T;
-    fp.eps = c.ln_eps; fp.scale = 1.0f / sqrtf(static_cast<float>(c.dec_dim_head));
-    fp.token0 = w.token0; fp.tok = tok; fp.v16 = v16; fp.q32 = q32; fp.att16 = att16; fp.hid16 = hid16;
-    fp.kv = kv; fp.kv_ld = L * 2 * inner; fp.barrier = dec_barrier;
-    S.push_back([fp](const RunCtx&, cudaStream_t st) -> int { return dec_fused_launch(fp, st); });
-  } else {
   {
     const float* t0 = w.token0;
     S.push_back([=](const RunCtx&, cudaStream_t st) -> int {
@@ -358,7 +343,6 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     ln(tok, dw.ln2_g, dw.ln2_b, y16, nullptr, B, E, c.ln_eps, 0, 0);
     linear(y16, E, B, dw.ff1_w, c.dec_mlp_dim, E, dw.ff1_b, kActGelu, nullptr, hid16);
     linear(hid16, c.dec_mlp_dim, B, dw.ff2_w, E, c.dec_mlp_dim, dw.ff2_b, kActNone, tok, nullptr, tok);
-  }
   }
   // decoder output: optional tap + fp16 operand copy for the read-outs and the classifier
   S.push_back([=](const RunCtx& r, cudaStream_t st) -> int {
@@ -483,6 +467,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
   if (err == THMR_OK) {
     cudaError_t ce = cudaMemsetAsync(p16, 0, static_cast<size_t>(B) * Lp0 * NC * sizeof(__half), stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(skf, 0, n_skf * sizeof(unsigned), stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(stamps, 0, kMaxStamps * sizeof(unsigned long long), stream);
     if (ce != cudaSuccess) *status = fail(THMR_ERR_CUDA, "cudaMemsetAsync(p16 / flags): %s", cudaGetErrorString(ce));
   }
   return total;

@@ -86,6 +86,7 @@ inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool b
 
   // ---------------------------------------------------------------- steps
   e->steps.clear();
+  e->stamps = nullptr;       // (in-graph stamps are a default-mode instrument)
   struct StepList {
     std::vector<Step>& v;
     const char* name = "";

@@ -93,7 +93,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int ksplit) {
-  static_assert(EPI == kEpiStore16 || EPI == kEpiAdd32 || EPI == kEpiStore32, "2-CTA GEMM supports the TMA epilogues only");
+  static_assert(EPI == kEpiStore16 || EPI == kEpiAdd32 || EPI == kEpiStore32, "CTA-pair GEMM supports the TMA epilogues only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kG2BarOffset);   // used in the leader only
@@ -114,6 +114,7 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int sk_tiles = (EPI == kEpiAdd32 && p.sk_flags != nullptr) ? p.sk_tiles : 0;
 
   pdl_launch_dependents();
+  stamp_start(p.stamp);
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -148,6 +149,8 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
+      const bool a_hint = (p.l2_hints & 1) != 0;
+      const uint64_t pol_a = l2_policy_evict_first();
       for (G2Work w(sk_tiles, tiles_m, tiles_n, num_kb, ksplit, cluster_id, num_clusters); w.valid(); w.next()) {
         const int m0 = w.m_blk() * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
         const int n0 = w.n_blk() * kG2BN + static_cast<int>(rank) * (kG2BN / 2);
@@ -166,7 +169,8 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           uint8_t* sa = smem + stage * kG2StageBytes;
           uint8_t* sb = sa + kG2ABytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
-          tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, m0);
+          if (a_hint) tma_load_2d_2sm_hint(sa, &tmA, &full_bar[stage], kb * kGemmBK, m0, pol_a);
+          else tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, m0);
           tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
         }
@@ -400,7 +404,8 @@ gemm_f16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 fence_proxy_async_all();
                 sk_waited = true;
               }
-              tma_reduce_add_2d(&tmC, slab_buf, col0, m0);
+              if (p.l2_hints & 4) tma_reduce_add_2d_hint(&tmC, slab_buf, col0, m0, l2_policy_evict_last());
+              else tma_reduce_add_2d(&tmC, slab_buf, col0, m0);
             }
             tma_store_commit();
           }

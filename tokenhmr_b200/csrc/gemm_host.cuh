@@ -4,7 +4,6 @@
 #include <stdlib.h>
 
 #include "gemm2_tcgen05.cuh"
-#include "gemm4_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace thmr {
@@ -16,7 +15,6 @@ struct GemmPlan {
   int epi;
   int grid;
   int two_cta;  // CTA-pair kernel (256 x 256 tiles)
-  int quad;     // CTA-quad kernel (two pairs per cluster, weight tile multicast): tmB then holds 64-row boxes
   int ksplit;   // split-K factor (reduce-add epilogue only)
 };
 
@@ -38,6 +36,8 @@ struct GemmDesc {
   int force_epi = -1;  // 0 forces the generic epilogue (tests)
   int force_2cta = -1; // -1 auto, 0 never, 1 always (when eligible)
   unsigned int* sk_flags = nullptr;  // >= gemm_sk_flag_count(M, N) zeroed uints: enables stream-K for reduce-add GEMMs
+  int a_dead = 0;    // the A operand is not read again after this GEMM: load it with the L2 evict_first policy
+  unsigned long long* stamp = nullptr;   // in-graph start stamp slot (nullable)
 };
 
 // Flags a stream-K GEMM of this shape needs (4 per 256 x 256 tile); the buffer must be zero before the first launch and
@@ -101,36 +101,6 @@ inline int pick_bn(int M, int N, int force, int epi) {
   return best;
 }
 
-// Co-resident clusters of four for the CTA-quad kernel (configures its shared-memory attribute on first use).
-template <int EPI>
-inline int quad_max_clusters_t() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  cached = 0;
-  if (cudaFuncSetAttribute(gemm_f16_tn_4cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemTotal) !=
-      cudaSuccess)
-    return cached;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(4 * 37, 1, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
-  cfg.dynamicSmemBytes = kG2SmemTotal;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_f16_tn_4cta_kernel<EPI>, &cfg) == cudaSuccess && n > 0) cached = n;
-  else { cudaGetLastError(); cached = 0; }
-  return cached;
-}
-inline int quad_max_clusters(int epi) {
-  if (epi == kEpiStore16) return quad_max_clusters_t<kEpiStore16>();
-  if (epi == kEpiAdd32) return quad_max_clusters_t<kEpiAdd32>();
-  if (epi == kEpiStore32) return quad_max_clusters_t<kEpiStore32>();
-  return 0;
-}
-
 inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   THMR_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "gemm: bad shape %dx%dx%d", d.M, d.N, d.K);
   THMR_CHECK(d.out32 || d.out16 || d.argmin_out, "gemm: no output");
@@ -149,6 +119,10 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   { const char* e = getenv("THMR_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("THMR_GEMM_COUNTERS"); p.dbg_counters = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   p.alpha = d.alpha; p.argmin_out = d.argmin_out; p.row_sq = d.row_sq; p.col_sq = d.col_sq;
+  // THMR_L2_HINTS bits: 1 = dead A operands evict_first, 2 = attention Q/K/V evict_first, 4 = reduce-add target evict_last
+  static const int env_hints = [] { const char* e = getenv("THMR_L2_HINTS"); return e ? atoi(e) : 0; }();
+  p.l2_hints = ((env_hints & 1) && d.a_dead ? 1 : 0) | (env_hints & 4);
+  p.stamp = d.stamp;
   const int num_kb = (d.K + kGemmBK - 1) / kGemmBK;
   uint64_t a_cols = d.K;
   if (d.taps > 1) {
@@ -166,18 +140,13 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   if (d.force_2cta == 1 || d.force_bn == 512) two = epi != kEpiGeneric && d.taps == 1;
   plan->two_cta = two ? 1 : 0;
   plan->ksplit = 1;
-  // CTA-quad kernel (gemm4_tcgen05.cuh): needs an even number of 256-row tiles to pair up; THMR_GEMM_QUAD=1 enables it
-  static const int env_quad = [] { const char* e = getenv("THMR_GEMM_QUAD"); return e ? atoi(e) : 0; }();
-  static const int env_splitk0 = [] { const char* e = getenv("THMR_GEMM_SPLITK"); return e ? atoi(e) : 0; }();
-  const bool quad = two && env_quad && !env_splitk0 && ((d.M + 255) / 256) % 2 == 0;
-  plan->quad = quad ? 1 : 0;
   THMR_TRY(make_tmap_2d_f16(&plan->tmA, d.A, d.a_rows, a_cols, d.lda, kGemmBM, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
-  const int b_box_rows = quad ? static_cast<int>(kG4BQuarterRows) : (two ? kG2BN / 2 : bn);
+  const int b_box_rows = two ? kG2BN / 2 : bn;
   THMR_TRY(make_tmap_2d_f16(&plan->tmB, d.B, d.N, d.K, d.ldb, b_box_rows, kGemmBK, CU_TENSOR_MAP_SWIZZLE_128B));
   plan->bn = two ? kG2BN : bn;
   plan->epi = epi;
   // output boxes: 32 rows per epilogue warp, or (CTA-pair kernel, default) one 128-row slab per column half
-  const uint32_t c_rows = (two && !quad && !(p.dbg & 128)) ? 128 : 32;
+  const uint32_t c_rows = (two && !(p.dbg & 128)) ? 128 : 32;
   if (epi == kEpiStore16)
     THMR_TRY(make_tmap_2d(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out16, d.M, d.N, d.ld16, c_rows, 64,
                           CU_TENSOR_MAP_SWIZZLE_128B));
@@ -186,13 +155,6 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
                           CU_TENSOR_MAP_SWIZZLE_128B));
   else
     plan->tmC = plan->tmA;
-  if (quad) {
-    const long supers = static_cast<long>((d.M + 511) / 512) * ((d.N + kG2BN - 1) / kG2BN);
-    const int clusters = quad_max_clusters(epi);
-    THMR_CHECK(clusters > 0, "gemm: the CTA-quad kernel cannot be scheduled on this device");
-    plan->grid = 4 * static_cast<int>(supers < clusters ? supers : clusters);
-    return THMR_OK;
-  }
   if (two) {
     const int clusters = num_sms() / 2;
     const long tiles = static_cast<long>((d.M + 255) / 256) * ((d.N + kG2BN - 1) / kG2BN);
@@ -265,20 +227,7 @@ inline int gemm2_launch_t(const GemmPlan& plan, cudaStream_t stream) {
   return THMR_OK;
 }
 
-template <int EPI>
-inline int gemm4_launch_t(const GemmPlan& plan, cudaStream_t stream) {
-  gemm_f16_tn_4cta_kernel<EPI><<<plan.grid, kGemmThreads, kG2SmemTotal, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
-  THMR_CUDA(cudaGetLastError());
-  return THMR_OK;
-}
-
 inline int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  if (plan.quad) {
-    if (plan.epi == kEpiStore16) return gemm4_launch_t<kEpiStore16>(plan, stream);
-    if (plan.epi == kEpiAdd32) return gemm4_launch_t<kEpiAdd32>(plan, stream);
-    if (plan.epi == kEpiStore32) return gemm4_launch_t<kEpiStore32>(plan, stream);
-    return fail(THMR_ERR_INVALID, "gemm: CTA-quad kernel needs a TMA epilogue");
-  }
   if (plan.two_cta) {
     if (plan.epi == kEpiStore16) return gemm2_launch_t<kEpiStore16>(plan, stream);
     if (plan.epi == kEpiAdd32) return gemm2_launch_t<kEpiAdd32>(plan, stream);

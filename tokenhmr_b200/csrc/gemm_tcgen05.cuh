@@ -55,6 +55,8 @@ struct GemmParams {
   // ([tile][cta rank][column half], zero between launches)
   unsigned int* sk_flags;
   int sk_tiles;   // trailing tiles scheduled stream-K (gemm2_tcgen05.cuh G2Work)
+  unsigned long long* stamp;   // in-graph start stamp (common.cuh stamp_start), nullable
+  int l2_hints;   // CTA-pair kernel: bit 0 = A operand loaded evict_first (dead after this GEMM), bit 2 = reduce-add evict_last
   unsigned long long* dbg_counters;  // optional [gridDim.x][8] cycle counters (scripts/dev_gemm_qkv.py)
   int dbg;                 // THMR_GEMM_DBG experiments: 1 = skip epilogue work, 2 = skip only the TMA store
 };
@@ -176,6 +178,13 @@ __device__ __forceinline__ void named_bar_sync_64(int id) {
 __device__ __forceinline__ void named_bar_sync_128(int id) {
   asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1,
+                                                       uint64_t policy) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
                :
@@ -209,6 +218,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
+  stamp_start(p.stamp);
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);

@@ -2,12 +2,13 @@
 // (tokenhmr/lib/models/smpl_wrapper.py:27-41) as four kernels:
 //
 //   smpl_pose_kernel    per pose: (Rodrigues) -> joint locations -> 24-joint kinematic chain -> relative
-//                       transforms A (3x4), posed joints, and the pose-blend feature (R - I) split into
-//                       fp16 hi/lo operands for the tensor-core pose-blend GEMM
-//   [tcgen05 GEMM]      pose offsets = pose_feature (B x 207) * posedirs (207 x 3V): split-fp16 (hi*hi + lo*hi +
-//                       hi*lo, operands pre-scaled by 2^10) gives ~2^-21 relative error with fp32 accumulation
-//   smpl_skin_kernel    per (vertex, pose): v_shaped = v_t + S beta; + pose offset; T = sum_k w_k A_jk (sparse
-//                       skinning weights, ELL); vertex = T [v;1]
+//                       transforms A (3x4), posed joints, and the blend feature [R - I (207) | betas (10) | 1] split
+//                       into fp16 hi/lo operands for the tensor-core blend GEMM
+//   [tcgen05 GEMM]      v_posed = feature (B x 218) * [posedirs ; shapedirs ; v_template] (218 x 3V): the shape blend
+//                       and the template ride in the same contraction as the pose blend (blend_shapes + pose offsets
+//                       of smplx.lbs in one pass); split-fp16 (hi*hi + lo*hi + hi*lo, operands pre-scaled by 2^10)
+//                       gives ~2^-21 relative error with fp32 accumulation
+//   smpl_skin_kernel    per (vertex, pose): T = sum_k w_k A_jk (sparse skinning weights, ELL); vertex = T [v_posed;1]
 //   smpl_joints_kernel  per pose: 45 smplx joints -> 25 OpenPose joints (joint_map) + 19 regressed extra
 //                       joints (sparse CSR regressor) ; optional camera translation + perspective projection
 //                       (tokenhmr.py:165-187, geometry.py:86-124)
@@ -19,8 +20,10 @@
 namespace thmr {
 
 constexpr int kSmplJ = 24;
-constexpr int kSmplPF = 207;        // (24-1)*9
-constexpr int kSmplPFPad = 208;     // fp16 row pitch must be a multiple of 8 elements
+constexpr int kSmplPF = 207;        // (24-1)*9 pose-blend features
+constexpr int kSmplFeatBeta = 207;  // feature columns [207, 217): betas;  217: the constant 1 (template)
+constexpr int kSmplFeatOne = 217;
+constexpr int kSmplPFPad = 224;     // feature row: 207 + 10 + 1, padded to a multiple of 16 (fp16 pitch, UMMA K step)
 constexpr float kSplitScale = 1024.0f;
 
 struct SmplModel {
@@ -30,7 +33,7 @@ struct SmplModel {
   float* shapedirs = nullptr;     // [V,3,nb]
   float* J_template = nullptr;    // [24,3]      = J_regressor . v_template
   float* J_shapedirs = nullptr;   // [24,3,nb]   = J_regressor . shapedirs
-  __half* posedirsT = nullptr;    // [3V, 3*208] fp16: [hi | hi | lo] of 1024 * posedirs^T
+  __half* posedirsT = nullptr;    // [3V, 3*224] fp16: [hi | hi | lo] of 1024 * [posedirs^T | shapedirs | v_template]
   int ell = 0;                    // max non-zeros per vertex of lbs_weights
   int* w_idx = nullptr;           // [V, ell]
   float* w_val = nullptr;         // [V, ell]
@@ -68,13 +71,19 @@ __global__ void smpl_jreg_kernel(const float* __restrict__ Jreg, const float* __
   }
 }
 
-// ---- init-time: posedirs (207, 3V) fp32 -> transposed split fp16 [3V, 624] ------------------------------
-__global__ void smpl_pack_posedirs_kernel(const float* __restrict__ posedirs, __half* __restrict__ out, int V3) {
+// ---- init-time: blend basis -> transposed split fp16 [3V, 3*224]: row n = (vertex, coordinate), columns
+//      [posedirs(207, n) | shapedirs(n, 0..nb) | v_template(n) | 0]
+__global__ void smpl_pack_posedirs_kernel(const float* __restrict__ posedirs, const float* __restrict__ shapedirs,
+                                          const float* __restrict__ v_template, int nb, __half* __restrict__ out, int V3) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long>(V3) * kSmplPFPad) return;
   const int k = i % kSmplPFPad;
   const int n = i / kSmplPFPad;
-  float v = (k < kSmplPF) ? posedirs[static_cast<size_t>(k) * V3 + n] * kSplitScale : 0.f;
+  float v = 0.f;
+  if (k < kSmplPF) v = posedirs[static_cast<size_t>(k) * V3 + n];
+  else if (k < kSmplFeatBeta + nb) v = shapedirs[static_cast<size_t>(n) * nb + (k - kSmplFeatBeta)];
+  else if (k == kSmplFeatOne) v = v_template[n];
+  v *= kSplitScale;
   const __half hi = __float2half_rn(v);
   const __half lo = __float2half_rn(v - __half2float(hi));
   __half* o = out + static_cast<size_t>(n) * (3 * kSmplPFPad);
@@ -139,8 +148,19 @@ smpl_pose_kernel(const float* __restrict__ pose, int pose2rot, const float* __re
         o[2 * kSmplPFPad + e] = hi;
       }
     } else {
+      // shape-blend features: betas (columns 207..216), the constant 1 that multiplies v_template (217), zero padding
       __half* o = pf16 + static_cast<size_t>(b) * (3 * kSmplPFPad);
-      o[kSmplPF] = o[kSmplPFPad + kSmplPF] = o[2 * kSmplPFPad + kSmplPF] = __float2half_rn(0.f);
+      for (int k = kSmplFeatBeta; k < kSmplPFPad; ++k) {
+        float v = 0.f;
+        if (k < kSmplFeatBeta + nb) v = betas[static_cast<size_t>(b) * nb + (k - kSmplFeatBeta)];
+        else if (k == kSmplFeatOne) v = 1.f;
+        v *= kSplitScale;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        o[k] = hi;
+        o[kSmplPFPad + k] = lo;
+        o[2 * kSmplPFPad + k] = hi;
+      }
     }
   }
   __syncwarp();
@@ -182,53 +202,43 @@ smpl_pose_kernel(const float* __restrict__ pose, int pose2rot, const float* __re
 }
 
 // ---- skinning: thread = vertex, block = 128 vertices x SKIN_POSES poses ---------------------------------
+// v_posed comes out of the blend GEMM (L2-resident chunk); the next pose's three coordinates are loaded while the current
+// pose is skinned.  The 24 relative transforms of each pose sit in shared memory (odd joint stride: distinct joints
+// hit distinct banks, equal joints broadcast).
 constexpr int kSkinPoses = 16;
-constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used): odd stride -> distinct joints hit distinct banks
+constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used)
 constexpr int kSkinThreads = 128;
 
 __global__ void __launch_bounds__(kSkinThreads)
-smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__ shapedirs, int nb,
-                 const int* __restrict__ w_idx, const float* __restrict__ w_val, int ell,
-                 const float* __restrict__ betas, const float* __restrict__ A, const float* __restrict__ offsets,
-                 long off_pitch, float* __restrict__ verts, long vert_pitch /* floats between poses */, int V, int B) {
+smpl_skin_kernel(const int* __restrict__ w_idx, const float* __restrict__ w_val, int ell, const float* __restrict__ A,
+                 const float* __restrict__ vposed, long off_pitch, float* __restrict__ verts,
+                 long vert_pitch /* floats between poses */, int V, int B) {
   __shared__ float sA[kSkinPoses][kSmplJ * kSkinAStride];
-  __shared__ float sB[kSkinPoses][16];
   const int p0 = blockIdx.y * kSkinPoses;
   const int np = (B - p0) < kSkinPoses ? (B - p0) : kSkinPoses;
   for (int i = threadIdx.x; i < np * kSmplJ * 12; i += kSkinThreads) {
     const int r = i % (kSmplJ * 12);
     sA[i / (kSmplJ * 12)][(r / 12) * kSkinAStride + r % 12] = A[static_cast<size_t>(p0) * kSmplJ * 12 + i];
   }
-  for (int i = threadIdx.x; i < np * nb; i += kSkinThreads) sB[i / nb][i % nb] = betas[static_cast<size_t>(p0) * nb + i];
   __syncthreads();
   const int v = blockIdx.x * kSkinThreads + threadIdx.x;
   if (v >= V) return;
-  float vt[3], sd[3][10];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    vt[c] = v_template[v * 3 + c];
-#pragma unroll
-    for (int l = 0; l < 10; ++l) sd[c][l] = (l < nb) ? shapedirs[(static_cast<size_t>(v) * 3 + c) * nb + l] : 0.f;
-  }
   // skinning weights of this vertex: registers when the ELL width is small (real SMPL: 4), else re-read
   constexpr int kEllReg = 8;
   int wi[kEllReg];
   float wv[kEllReg];
 #pragma unroll
   for (int k = 0; k < kEllReg; ++k) {
-    wi[k] = (k < ell) ? w_idx[static_cast<size_t>(v) * ell + k] : 0;
+    wi[k] = (k < ell) ? w_idx[static_cast<size_t>(v) * ell + k] * kSkinAStride : 0;
     wv[k] = (k < ell) ? w_val[static_cast<size_t>(v) * ell + k] : 0.f;
   }
+  const float* src = vposed + static_cast<size_t>(p0) * off_pitch + v * 3;
+  float nx0 = src[0], nx1 = src[1], nx2 = src[2];
   for (int pp = 0; pp < np; ++pp) {
-    const int b = p0 + pp;
-    const float* off = offsets + static_cast<size_t>(b) * off_pitch + v * 3;
-    float x[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float s = vt[c];
-#pragma unroll
-      for (int l = 0; l < 10; ++l) s += sd[c][l] * sB[pp][l];
-      x[c] = s + off[c];
+    const float x0 = nx0, x1 = nx1, x2 = nx2;
+    if (pp + 1 < np) {
+      const float* nsrc = src + static_cast<size_t>(pp + 1) * off_pitch;
+      nx0 = nsrc[0]; nx1 = nsrc[1]; nx2 = nsrc[2];
     }
     float T[12];
 #pragma unroll
@@ -238,9 +248,9 @@ smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__
       for (int k = 0; k < kEllReg; ++k) {
         if (k < ell) {
           const float w = wv[k];
-          const float* a = &sA[pp][wi[k] * kSkinAStride];
+          const float* a = &sA[pp][wi[k]];
 #pragma unroll
-          for (int e = 0; e < 12; ++e) T[e] += w * a[e];
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(w, a[e], T[e]);
         }
       }
     } else {
@@ -248,12 +258,12 @@ smpl_skin_kernel(const float* __restrict__ v_template, const float* __restrict__
         const float w = w_val[static_cast<size_t>(v) * ell + k];
         const float* a = &sA[pp][w_idx[static_cast<size_t>(v) * ell + k] * kSkinAStride];
 #pragma unroll
-        for (int e = 0; e < 12; ++e) T[e] += w * a[e];
+        for (int e = 0; e < 12; ++e) T[e] = fmaf(w, a[e], T[e]);
       }
     }
-    float* o = verts + static_cast<size_t>(b) * vert_pitch + v * 3;
+    float* o = verts + static_cast<size_t>(p0 + pp) * vert_pitch + v * 3;
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr) o[rr] = T[rr * 4 + 0] * x[0] + T[rr * 4 + 1] * x[1] + T[rr * 4 + 2] * x[2] + T[rr * 4 + 3];
+    for (int rr = 0; rr < 3; ++rr) o[rr] = T[rr * 4 + 0] * x0 + T[rr * 4 + 1] * x1 + T[rr * 4 + 2] * x2 + T[rr * 4 + 3];
   }
 }
 

@@ -432,7 +432,8 @@ int thmr_smpl_create(const thmr_smpl_desc* d, thmr_smpl** out) {
   }
   {
     const long n = static_cast<long>(3) * V * kSmplPFPad;
-    smpl_pack_posedirs_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(pd, m.posedirsT, 3 * V);
+    smpl_pack_posedirs_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(pd, m.shapedirs, m.v_template, nb,
+                                                                               m.posedirsT, 3 * V);
   }
   cudaError_t ce = cudaDeviceSynchronize();
   cudaFree(Jreg);
@@ -586,6 +587,23 @@ int thmr_engine_forward(thmr_engine* e, const float* img, int B, const thmr_outp
   RunCtx ctx{img, *out, nullptr};
   for (auto& step : e->steps) THMR_TRY(step.fn(ctx, st));
   return THMR_OK;
+}
+
+int thmr_engine_forward_stamped(thmr_engine* e, const float* img, int B, const thmr_outputs* out, void* workspace,
+                                void* stream) {
+  THMR_TRY(thmr_engine_forward(e, img, B, out, workspace, stream));
+  THMR_CHECK(e->stamps != nullptr, "forward_stamped: this engine mode records no stamps");
+  stamp_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(e->stamps + e->steps.size());
+  THMR_CUDA(cudaGetLastError());
+  return THMR_OK;
+}
+
+int thmr_engine_read_stamps(const thmr_engine* e, unsigned long long* host_ns, int cap) {
+  THMR_CHECK(e && host_ns && e->stamps, "read_stamps: no stamps");
+  const int n = static_cast<int>(e->steps.size()) + 1;
+  THMR_CHECK(cap >= n && n <= kMaxStamps, "read_stamps: need room for %d entries", n);
+  THMR_CUDA(cudaMemcpy(host_ns, e->stamps, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 int thmr_engine_vit_forward(thmr_engine* e, const float* img, int B, float* tokens, void* workspace, void* stream) {

@@ -262,6 +262,46 @@ class TokenHMREngine(nn.Module):
             return out
 
     @torch.no_grad()
+    def profile_in_graph(self, img: torch.Tensor, replays: int = 20) -> list:
+        """Per-step device time INSIDE the CUDA-graph replay: every kernel of the forward stamps the GPU's nanosecond timer
+        when it starts (thmr_engine_forward_stamped); `replays` back-to-back replays of that graph keep the chip in its
+        sustained state and the stamps of the last one are read.  Returns [(label, ms, flops, bytes), ...] like profile();
+        a step without a stamped kernel reports 0 and its time is part of the step before it.  The entries sum to the
+        replay's duration: unlike the event-separated profile() nothing is inserted between the launches."""
+        B = img.shape[0]
+        with torch.cuda.device(self.device):
+            st = self._state(B, False, slot=-1)
+            st["t"]["img"].copy_(img.to(torch.float32))
+            stream = lambda: torch.cuda.current_stream().cuda_stream
+            launch = lambda: check(lib().thmr_engine_forward_stamped(self._h, st["t"]["img"].data_ptr(), B,
+                                                                     ctypes.byref(st["outs"]), st["ws_ptr"], stream()))
+            if st["graph"] is None:
+                launch()
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch()
+                st["graph"] = g
+            for _ in range(max(1, replays)):
+                st["graph"].replay()
+            torch.cuda.current_stream().synchronize()
+            n = lib().thmr_engine_num_steps(self._h)
+            buf = (ctypes.c_uint64 * (n + 1))()
+            got = lib().thmr_engine_read_stamps(self._h, buf, n + 1)
+            if got != n + 1:
+                check(got if got < 0 else -1)
+            t = [int(v) for v in buf]
+            out, starts = [], [i for i in range(n) if t[i] != 0] + [n]
+            dur = {i: 0.0 for i in range(n)}
+            for a, b in zip(starts[:-1], starts[1:]):
+                dur[a] = (t[b] - t[a]) * 1e-6
+            for i in range(n):
+                name, fl, by = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_double()
+                check(lib().thmr_engine_step_info(self._h, i, ctypes.byref(name), ctypes.byref(fl), ctypes.byref(by)))
+                out.append((name.value.decode(), dur[i], fl.value, by.value))
+            return out
+
+    @torch.no_grad()
     def backbone(self, img: torch.Tensor) -> torch.Tensor:
         """ViT.forward (vit.py:341-343): (B,3,256,256) -> (B,1280,16,12) like the reference backbone."""
         B = img.shape[0]
