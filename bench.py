@@ -106,9 +106,9 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        pw = sorted(float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit())
+        # (power.draw is a ~1 s moving average: meaningless over a 0.4 s window; scripts/dev_sustained.py reads it over 2 s runs)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
+                "samples": len(sm)}
 
 
 # ---------------------------------------------------------------------------------------------------------
