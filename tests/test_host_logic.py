@@ -60,3 +60,26 @@ def test_shard_range_covers_batch_contiguously():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_split_weight_layout_and_precision():
+    """Host half of the split-precision contractions (strict mode, tokenizer encoder): w * 2^8 = hi + lo with
+    hi = fp16(w * 2^8), lo = fp16(w * 2^8 - hi); packed per tap as [hi | hi | lo]."""
+    import torch
+    from tokenhmr_b200._lib import ThmrError
+    from tokenhmr_b200.weights import STRICT_W_SCALE, split_weight
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 3 * 16, generator=g) * 0.3
+    w[0, 0], w[1, 5] = 1e-7, 200.0                                   # tiny and large magnitudes
+    s = split_weight(w, taps=3)
+    assert s.dtype == torch.float16 and tuple(s.shape) == (8, 3 * 3 * 16)
+    s = s.float().view(8, 3, 3, 16)                                  # [out, tap, (hi | hi | lo), cin]
+    assert torch.equal(s[:, :, 0], s[:, :, 1])
+    rec = (s[:, :, 0] + s[:, :, 2]).reshape(8, 48) / STRICT_W_SCALE
+    err = (rec - w).abs()
+    assert (err <= w.abs() * 2.0 ** -21 + 2.0 ** -33).all(), err.max()
+    one = split_weight(w, taps=1).float()
+    assert torch.equal(one[:, :48], one[:, 48:96])                   # single tap: [hi(48) | hi(48) | lo(48)]
+    import pytest
+    with pytest.raises(ThmrError):
+        split_weight(torch.full((2, 4), 300.0))
