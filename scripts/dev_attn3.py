@@ -1,5 +1,7 @@
 """Two-chain attention kernel: timing + per-role cycle counters."""
 import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 dev = torch.device("cuda:0"); torch.manual_seed(0)
