@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace thmr {
 
@@ -55,11 +56,17 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, __half* __res
 //       y16[(r / T) * C * T + c * T + (r % T)]   (MixerLayer token mixing, modules.py:56-59)
 //   Row pitch of the fp16 output is ld16 (elements) when not transposed.
 // ------------------------------------------------------------------------------------------------
-template <int VEC4, bool PREFETCH>  // float4 loads per lane; PREFETCH: the next row's loads are issued before this row's math
+// PLAIN16: the ViT's case (fp16 output only, no ReLU, not transposed, C == 128 * VEC4 exactly), compiled without the other
+// output modes' branches and without the per-chunk column guards.
+template <int VEC4, bool PREFETCH, bool PLAIN16 = false>  // float4 loads per lane; PREFETCH: the next row's loads are issued before this row's math
 __global__ void __launch_bounds__(256, VEC4 > 10 ? (PREFETCH ? 1 : 2) : (PREFETCH ? 2 : 4))
 layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     __half* __restrict__ y16, int ld16, float* __restrict__ y32, int R, int C, float eps, int relu,
-                     int out_t, unsigned long long* stamp) {
+                     __half* __restrict__ y16, int ld16, float* __restrict__ y32_, int R, int C_, float eps, int relu_,
+                     int out_t_, unsigned long long* stamp) {
+  const int C = PLAIN16 ? VEC4 * 128 : C_;
+  float* const y32 = PLAIN16 ? nullptr : y32_;
+  const int relu = PLAIN16 ? 0 : relu_;
+  const int out_t = PLAIN16 ? 0 : out_t_;
   stamp_start(stamp);
   // gamma/beta staged in shared memory once per (persistent) block: read from global inside the output loop they
   // were the largest stall of the kernel (an L2-latency load per 4 outputs, after the reductions)
@@ -80,7 +87,7 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 #pragma unroll
     for (int i = 0; i < VEC4; ++i) {
       const int c = (i * 32 + lane) * 4;
-      v[i] = (c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = (PLAIN16 || c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   // persistent warps: the grid is sized to the resident capacity and every warp walks rows with a grid stride
@@ -94,31 +101,48 @@ layernorm_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     } else {
       load_row(v, warp);
     }
-    float s = 0.f;
+    // Packed fp32 (FFMA2: two IEEE lanes per instruction) for the three arithmetic passes: the kernel issues ~320
+    // instructions per lane and row and sits at 60 % issue utilisation next to its HBM stalls (ncu); packing takes it to ~200.
+    // Rows shorter than the register tile hold zeros beyond C (they add 0 to the sum; the variance pass masks them).
+    uint64_t s2 = f2_pack(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < VEC4; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
+    for (int i = 0; i < VEC4; ++i) {
+      s2 = f2_add(s2, f2_pack(v[i].x, v[i].y));
+      s2 = f2_add(s2, f2_pack(v[i].z, v[i].w));
+    }
+    float s_lo, s_hi;
+    f2_unpack(s2, s_lo, s_hi);
+    const float mean = warp_sum(s_lo + s_hi) / C;
+    const uint64_t nmean2 = f2_pack(-mean, -mean);
+    uint64_t q2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < VEC4; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < C) {
-        const float a = v[i].x - mean, b = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
-        q += a * a + b * b + d * d + e * e;
+      if (PLAIN16 || c < C) {
+        const uint64_t d0 = f2_add(f2_pack(v[i].x, v[i].y), nmean2);
+        const uint64_t d1 = f2_add(f2_pack(v[i].z, v[i].w), nmean2);
+        q2 = f2_fma(d0, d0, q2);
+        q2 = f2_fma(d1, d1, q2);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    float q_lo, q_hi;
+    f2_unpack(q2, q_lo, q_hi);
+    const float rstd = rsqrtf(warp_sum(q_lo + q_hi) / C + eps);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
 #pragma unroll
     for (int i = 0; i < VEC4; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < C) {
+      if (PLAIN16 || c < C) {
         const float4 g = sg[c >> 2];
         const float4 bb = sb[c >> 2];
+        // ((x - mean) * rstd) * g + b, the reference's order of operations
+        const uint64_t t0 = f2_mul(f2_add(f2_pack(v[i].x, v[i].y), nmean2), rstd2);
+        const uint64_t t1 = f2_mul(f2_add(f2_pack(v[i].z, v[i].w), nmean2), rstd2);
+        const uint64_t o0 = f2_fma(t0, f2_pack(g.x, g.y), f2_pack(bb.x, bb.y));
+        const uint64_t o1 = f2_fma(t1, f2_pack(g.z, g.w), f2_pack(bb.z, bb.w));
         float4 o;
-        o.x = (v[i].x - mean) * rstd * g.x + bb.x;
-        o.y = (v[i].y - mean) * rstd * g.y + bb.y;
-        o.z = (v[i].z - mean) * rstd * g.z + bb.z;
-        o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+        f2_unpack(o0, o.x, o.y);
+        f2_unpack(o1, o.z, o.w);
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (y32) {
           if (out_t > 0) {   // transposed inside groups of out_t rows, like the fp16 output (strict mode operand)
@@ -226,10 +250,13 @@ inline int layernorm_launch(const float* x, const float* gamma, const float* bet
     THMR_CHECK(C % 4 == 0, "layernorm: C must be a multiple of 4");
     const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
     const int vec4 = (C / 4 + 31) / 32;
+    const bool plain16 = y16 && !y32 && !relu && out_t == 0 && C == 128 * vec4 && !prefetch;
 #define THMR_LN_LAUNCH(V)                                                                                           \
   do {                                                                                                             \
     if (prefetch) THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, true>, grid, threads, smem, st, x, gamma, beta, y16, \
                                        ld16, y32, R, C, eps, relu, out_t, stamp));                                 \
+    else if (plain16 && V == vec4) THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, false, true>, grid, threads, smem,  \
+                                       st, x, gamma, beta, y16, ld16, y32, R, C, eps, relu, out_t, stamp));        \
     else THMR_CUDA(launch_pdl(layernorm_reg_kernel<V, false>, grid, threads, smem, st, x, gamma, beta, y16, ld16,   \
                               y32, R, C, eps, relu, out_t, stamp));                                                \
   } while (0)

@@ -128,30 +128,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // gelu_erf, rearranged so that everything but |x|, max and the reciprocal is packed:
 //   t = -0.5|x|,  a = |x|/sqrt(2) = t * (-sqrt(2)),  r = 1 / (1 + c1 a + ... + c6 a^6)^16,  gelu = max(x, 0) + t * r
 // 18 issue slots per PAIR instead of ~17 per element: the fc1 epilogue (63 M GELUs per layer) is issue-bound.
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_splat(float c) { return f2_pack(c, c); }
 // x = (x0, x1) packed -> (gelu(x0), gelu(x1)) packed
 __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
   float x0, x1;
