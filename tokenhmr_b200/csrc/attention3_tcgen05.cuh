@@ -139,7 +139,8 @@ __device__ __forceinline__ float att3_pass1(uint32_t tb, float* dbg_row) {
 
 template <int POLY, bool DBG>
 __global__ void __launch_bounds__(kAtt3Threads, 1)
-vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
+vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQK64,
+                      const __grid_constant__ CUtensorMap tmQK16, const __grid_constant__ CUtensorMap tmO,
                       const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -159,6 +160,10 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const int lane = threadIdx.x & 31;
   const bool dup_alt = !(p.p_in_tmem & 1);     // experiment knobs (THMR_ATTN_TS): bit 0 = fixed duplicate rows
   const bool use_turns = !(p.p_in_tmem & 8);   // bit 3 = no exp-phase alternation between the chains
+  // Q and K arrive as one [192 x 64] SWIZZLE_128B box (dims 0..63: four of the five 16-wide UMMA k-chunks) plus one
+  // [192 x 16] SWIZZLE_32B box: 384 TMA row requests per matrix instead of the 960 32-byte requests of five chunk boxes
+  // (the MMA issuers spent 15 % of the kernel waiting for the next head's Q, K).  Bit 5 = the round-1 five-chunk layout.
+  const bool wide_qk = !(p.p_in_tmem & 32);
   const int nheads = (p.num_problems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                      static_cast<int>(gridDim.x);
 
@@ -166,6 +171,8 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   stamp_start(p.stamp);
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQK64);
+    tma_prefetch_desc(&tmQK16);
     tma_prefetch_desc(&tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1);
@@ -206,7 +213,13 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         if (lane == 0) {
           mbar_wait(&qk_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&qk_full[st], 2 * kAttMatBytes);
-          if (hint) {
+          if (wide_qk) {
+            const int cq = h * kAttHeadDim, ck = (p.heads + h) * kAttHeadDim;
+            tma_load_2d(sQ, &tmQK64, &qk_full[st], cq, b * kAttTokens);
+            tma_load_2d(sQ + kAttWideBytes, &tmQK16, &qk_full[st], cq + 64, b * kAttTokens);
+            tma_load_2d(sQ + kAttMatBytes, &tmQK64, &qk_full[st], ck, b * kAttTokens);
+            tma_load_2d(sQ + kAttMatBytes + kAttWideBytes, &tmQK16, &qk_full[st], ck + 64, b * kAttTokens);
+          } else if (hint) {
             tma_load_3d_hint(sQ, &tmQKV, &qk_full[st], 0, b * kAttTokens, h * kAttChunks, pol);
             tma_load_3d_hint(sQ + kAttMatBytes, &tmQKV, &qk_full[st], 0, b * kAttTokens, (p.heads + h) * kAttChunks, pol);
           } else {
@@ -250,8 +263,17 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         if (elect_one()) {
 #pragma unroll
           for (int kc = 0; kc < kAttChunks; ++kc) {
-            const uint64_t da = make_smem_desc(sQ + kc * kAttChunkBytes + row0 * 32, 16, 256, kSwz32);
-            const uint64_t db = make_smem_desc(sQ + kAttMatBytes + kc * kAttChunkBytes, 16, 256, kSwz32);
+            uint64_t da, db;
+            if (wide_qk && kc < 4) {           // k-chunk kc = bytes [32 kc, 32 kc + 32) of the 128-byte rows
+              da = make_smem_desc(sQ + row0 * 128 + kc * 32, 16, 1024, kSwz128);
+              db = make_smem_desc(sQ + kAttMatBytes + kc * 32, 16, 1024, kSwz128);
+            } else if (wide_qk) {
+              da = make_smem_desc(sQ + kAttWideBytes + row0 * 32, 16, 256, kSwz32);
+              db = make_smem_desc(sQ + kAttMatBytes + kAttWideBytes, 16, 256, kSwz32);
+            } else {
+              da = make_smem_desc(sQ + kc * kAttChunkBytes + row0 * 32, 16, 256, kSwz32);
+              db = make_smem_desc(sQ + kAttMatBytes + kc * kAttChunkBytes, 16, 256, kSwz32);
+            }
             umma_f16_ss(tb, da, db, idesc_s, kc != 0);
           }
           umma_commit(&s_full[g]);
@@ -352,6 +374,11 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tmem_pin(o0);
         tmem_pin(o1);
         tmem_pin(o2);
+        // O is in registers: hand the tile buffer back NOW, so that the next tile's S = Q K^T is issued while this warp
+        // still converts, stages and stores its rows (the arrive used to sit at the end of the epilogue, ~600 cycles later)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[g]);
         const float inv = 1.0f / sum;
         auto pack8 = [&](const uint32_t* v) {
           uint4 w;
@@ -381,10 +408,11 @@ vit_attention3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           tma_store_commit();
         }
         c_epi += clock64() - t1;
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[g]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[g]);
     }
     if (lane == 0) tma_store_wait_read<0>();
     if (p.dbg_counters && lane == 0 && (warp == 2 || warp == 6)) {
@@ -410,8 +438,8 @@ inline int attention3_launch_t(const AttnPlan& plan, cudaStream_t st) {
                                    kAtt3SmemBytes));
     configured = true;
   }
-  THMR_CUDA(launch_pdl(vit_attention3_kernel<POLY, DBG>, plan.grid, kAtt3Threads, kAtt3SmemBytes, st, plan.tm, plan.tm_out,
-                       plan.p));
+  THMR_CUDA(launch_pdl(vit_attention3_kernel<POLY, DBG>, plan.grid, kAtt3Threads, kAtt3SmemBytes, st, plan.tm, plan.tm_qk64,
+                       plan.tm_qk16, plan.tm_out, plan.p));
   return THMR_OK;
 }
 

@@ -16,6 +16,7 @@ constexpr int kAttHeadDim = 80;
 constexpr int kAttChunks = kAttHeadDim / 16;                     // 16-element (32 B) K-chunks
 constexpr uint32_t kAttChunkBytes = kAttTokens * 32;             // 6144
 constexpr uint32_t kAttMatBytes = kAttChunks * kAttChunkBytes;   // 30720 (one of Q / K / V)
+constexpr uint32_t kAttWideBytes = kAttTokens * 128;             // 24576: the [192 x 64] SWIZZLE_128B block of Q / K
 
 struct AttnParams {
   int num_problems;  // B * H
@@ -55,6 +56,8 @@ inline int make_tmap_qkv(CUtensorMap* out, const void* qkv, uint64_t rows, uint6
 }
 
 struct AttnPlan {
+  CUtensorMap tm_qk64;  // Q / K: [192 rows x 64 columns] boxes, 128-byte rows, SWIZZLE_128B (dims 0..63 of a head)
+  CUtensorMap tm_qk16;  // Q / K: [192 rows x 16 columns] boxes, SWIZZLE_32B (dims 64..79)
   CUtensorMap tm;
   CUtensorMap tm_out;   // [B*192, H*80] fp16 output, 32-row x 80-column boxes (third-generation kernel)
   AttnParams p;
@@ -67,6 +70,10 @@ inline int attention_make_plan(const __half* qkv, int ld_qkv, int B, int heads, 
   THMR_CHECK(ld_qkv >= 3 * heads * kAttHeadDim, "attention: qkv pitch %d < %d", ld_qkv, 3 * heads * kAttHeadDim);
   THMR_CHECK(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: output alignment");
   THMR_TRY(make_tmap_qkv(&plan->tm, qkv, static_cast<uint64_t>(B) * kAttTokens, ld_qkv));
+  THMR_TRY(make_tmap_2d_f16(&plan->tm_qk64, qkv, static_cast<uint64_t>(B) * kAttTokens, static_cast<uint64_t>(ld_qkv), ld_qkv,
+                            kAttTokens, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+  THMR_TRY(make_tmap_2d_f16(&plan->tm_qk16, qkv, static_cast<uint64_t>(B) * kAttTokens, static_cast<uint64_t>(ld_qkv), ld_qkv,
+                            kAttTokens, 16, CU_TENSOR_MAP_SWIZZLE_32B));
   THMR_TRY(make_tmap_2d_f16(&plan->tm_out, out, static_cast<uint64_t>(B) * kAttTokens,
                             static_cast<uint64_t>(heads) * kAttHeadDim, ldo, 32, kAttHeadDim, CU_TENSOR_MAP_SWIZZLE_NONE));
   plan->p.num_problems = B * heads;
