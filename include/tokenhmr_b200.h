@@ -231,6 +231,10 @@ typedef struct thmr_config {
                  * products, ~2^-21 relative = fp32-grade, the reference's arithmetic: demo.py:35-37 runs fp32); all
                  * "w" matrices of thmr_weights are then f16 [out, 3*in] = [hi | hi | lo] of w * 2^8 (per tap for convs),
                  * as packed by tokenhmr_b200/weights.py with strict=True. */
+  int concurrent; /* 0: the forward owns the GPU while it runs (default).  1: its kernels may share the GPU with other work
+                   * (another forward of this engine's weights replayed on a second stream, TokenHMRPipeline(streams=2)):
+                   * schedules that need every CTA of a grid to be resident at the same time (the stream-K reduce-add GEMM,
+                   * whose CTA pairs wait for each other's partial tiles) are replaced by their whole-tile forms. */
 } thmr_config;
 
 /* Weight pointers, packed by the host loader (tokenhmr_b200/weights.py) from the reference state_dicts.

@@ -175,6 +175,43 @@ def test_pipeline_matches_synchronous_forward(tiny):
             assert torch.equal(g[k], w[k]), k
 
 
+def test_two_stream_pipeline_matches_synchronous_forward(cuda_dev):
+    """TokenHMRPipeline(streams=2): the forwards of consecutive batches replay on two streams and overlap on the SMs
+    (engine built with concurrent=True).  Every batch must still come back bit-identical to the synchronous forward of the
+    same engine; a pipeline on an engine without the flag, or with more streams than slots, is refused."""
+    from tokenhmr_b200 import _lib, synth
+    from tokenhmr_b200.config import tiny_config
+    from tokenhmr_b200.engine import TokenHMREngine, TokenHMRPipeline
+    cfg = tiny_config(vit_depth=2)
+    sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
+    model = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=False, concurrent=True)
+    keys = ("pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t")
+    batches = [synth.make_images(8, cfg, seed=60 + i).pin_memory() for i in range(9)]
+    want = []
+    for b in batches:
+        out = model({"img": b})
+        want.append({k: out[k].cpu().clone() for k in keys})
+    model.use_cuda_graph = True
+    for depth in (2, 3):
+        pipe = TokenHMRPipeline(model, depth=depth, read_back=keys, streams=2)
+        tickets = []
+        got = []
+        for b in batches:
+            tickets.append(pipe.submit({"img": b}))
+            if len(tickets) >= depth:
+                got.append({k: v.clone() for k, v in pipe.result(tickets[len(got)]).items()})
+        while len(got) < len(batches):
+            got.append({k: v.clone() for k, v in pipe.result(tickets[len(got)]).items()})
+        for g, w in zip(got, want):
+            for k in keys:
+                assert torch.equal(g[k], w[k]), (depth, k)
+    plain = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=True)
+    with pytest.raises(_lib.ThmrError):
+        TokenHMRPipeline(plain, depth=2, streams=2)
+    with pytest.raises(_lib.ThmrError):
+        TokenHMRPipeline(model, depth=2, streams=3)
+
+
 def test_release_forward_vs_reference_golden(cuda_dev, golden_dir):
     """Full ViT-H/16 depth-32 forward (B=2) against the outputs of the LIVE reference modules (fp32)."""
     from tokenhmr_b200 import synth

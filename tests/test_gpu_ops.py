@@ -202,6 +202,56 @@ def test_vq_quantize_1m_queries_round_trip(cuda_dev):
     assert torch.equal(ops.vq_quantize(ops.vq_dequantize(idx, cb), cb), idx)
 
 
+def _vq_both(x, cb):
+    """(screened, exact) indices of the two arithmetically equivalent schedules of thmr_vq_argmin (csrc/vq.cuh)."""
+    import os
+    from tokenhmr_b200 import ops
+    prev = os.environ.get("THMR_VQ_SCREEN")
+    try:
+        os.environ["THMR_VQ_SCREEN"] = "1"
+        a = ops.vq_quantize(x, cb)
+        os.environ["THMR_VQ_SCREEN"] = "0"
+        b = ops.vq_quantize(x, cb)
+    finally:
+        if prev is None:
+            os.environ.pop("THMR_VQ_SCREEN", None)
+        else:
+            os.environ["THMR_VQ_SCREEN"] = prev
+    return a, b
+
+
+def test_vq_screened_equals_exact(cuda_dev):
+    """The screened arg-min (one fp16 product per pair, rows whose top-2 margin does not clear the rigorous error bound
+    re-done by the exact 3-product pass) must return the SAME index as the exact pass on every row: unstructured queries
+    (~11 % re-done), queries next to a code (none re-done), several pass-1 chunks, ragged row counts, a codebook of
+    identical codes (every row re-done, more rows than one exact-pass round holds: first minimum = 0) and duplicated
+    codes."""
+    g = torch.Generator(cuda_dev).manual_seed(11)
+    cb = torch.randn(2048, 256, device=cuda_dev, generator=g)
+    for Q in (8192, 100_003, 300_001):
+        x = torch.randn(Q, 256, device=cuda_dev, generator=g)
+        a, b = _vq_both(x, cb)
+        assert torch.equal(a, b), (Q, int((a != b).sum()))
+    pick = torch.randint(0, 2048, (150_000,), device=cuda_dev, generator=g)
+    near = cb[pick] + 0.05 * torch.randn(150_000, 256, device=cuda_dev, generator=g)
+    a, b = _vq_both(near, cb)
+    assert torch.equal(a, b) and torch.equal(a, pick)
+    # scaled-up data (larger norms -> larger margins and bounds alike) and tiny data
+    for scale in (7.0, 1e-3):
+        x = scale * torch.randn(50_000, 256, device=cuda_dev, generator=g)
+        a, b = _vq_both(x, scale * cb)
+        assert torch.equal(a, b), scale
+    same = cb[:1].expand(2048, 256).contiguous()
+    x = torch.randn(300_001, 256, device=cuda_dev, generator=g)
+    a, b = _vq_both(x, same)
+    assert torch.equal(a, b) and int(a.abs().max()) == 0
+    cb2 = cb.clone()
+    cb2[1500] = cb2[20]
+    x = cb2[torch.randint(0, 2048, (20_000,), device=cuda_dev, generator=g)] + 0.01 * torch.randn(20_000, 256, device=cuda_dev, generator=g)
+    a, b = _vq_both(x, cb2)
+    assert torch.equal(a, b) and int((a == 1500).sum()) == 0
+
+
 # ------------------------------------------------------------------------------------------------ geometry / SMPL
 def test_rot6d_golden(cuda_dev, golden_dir):
     from tokenhmr_b200 import ops
@@ -243,6 +293,29 @@ def test_lbs_vs_oracle_and_fixture(cuda_dev, smpl_pair, golden_dir):
     assert rel_err(cam_t, want_t) < 1e-6 and torch.equal(focal.cpu(), torch.full((8, 2), 5000.0))
     want2d = O.perspective_projection(torch.from_numpy(g["joints"]), want_t, torch.full((8, 2), 5000.0 / 256))
     assert rel_err(kp2d, want2d) < 1e-4
+
+
+def test_lbs_skin_launch_shapes_agree(cuda_dev, smpl_pair):
+    """The skinning kernel's two launch shapes (128 / 256 vertices per block, THMR_SKIN_THREADS) do the same arithmetic:
+    bit-identical vertices, also across the 512-pose chunk boundary and for a ragged last pose tile."""
+    import os
+    smpl, m = smpl_pair
+    torch.manual_seed(9)
+    aa = 0.3 * torch.randn(1100 + 7, 24, 3, device=cuda_dev)
+    betas = torch.randn(1100 + 7, 10, device=cuda_dev)
+    got = {}
+    prev = os.environ.get("THMR_SKIN_THREADS")
+    try:
+        for t in ("128", "256"):
+            os.environ["THMR_SKIN_THREADS"] = t
+            v, j = m.lbs(betas, aa, pose2rot=True)
+            got[t] = (v.clone(), j.clone())
+    finally:
+        if prev is None:
+            os.environ.pop("THMR_SKIN_THREADS", None)
+        else:
+            os.environ["THMR_SKIN_THREADS"] = prev
+    assert torch.equal(got["128"][0], got["256"][0]) and torch.equal(got["128"][1], got["256"][1])
 
 
 def test_lbs_identity_pose_and_batch_4096(cuda_dev, smpl_pair):

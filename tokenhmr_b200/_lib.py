@@ -34,7 +34,7 @@ class Config(Structure):
                 ("cls_token_inter", c_int), ("cls_blocks", c_int),
                 ("code_dim", c_int), ("tok_width", c_int), ("tok_depth", c_int), ("tok_dilation_rate", c_int),
                 ("tok_joints", c_int), ("n_upsample", c_int), ("upsample_sizes", c_int * 8),
-                ("focal_length", c_float), ("strict", c_int)]
+                ("focal_length", c_float), ("strict", c_int), ("concurrent", c_int)]
 
 
 class VitBlock(Structure):

@@ -76,6 +76,9 @@ inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const 
                     float* cam_t, float* focal_out, float* kp2d, const SmplWs& ws, const GemmPlan* blend_plans,
                     cudaStream_t st) {
   const SmplModel& m = sm->m;
+  // vertices per skinning block (smpl_lbs.cuh); read per call so that a benchmark can compare the shapes in one process
+  int skin_threads = kSkinThreadsDefault;
+  { const char* e = getenv("THMR_SKIN_THREADS"); if (e && (atoi(e) == 128 || atoi(e) == 256)) skin_threads = atoi(e); }
   smpl_pose_kernel<<<B, 32, 0, st>>>(pose, pose2rot, betas, m.J_template, m.J_shapedirs, m.nb, sm->parents_dev, ws.A,
                                      lbs_joints ? lbs_joints : ws.Jposed, ws.pf16, B);
   THMR_CUDA(cudaGetLastError());
@@ -86,10 +89,17 @@ inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const 
     const GemmPlan* plan = blend_plans ? &blend_plans[ci] : &local;
     if (!blend_plans) THMR_TRY(smpl_blend_plan(m, ws, p0, n, &local));
     THMR_TRY(gemm_launch(*plan, st));
-    dim3 grid((m.V + kSkinThreads - 1) / kSkinThreads, (n + kSkinPoses - 1) / kSkinPoses);
-    smpl_skin_kernel<<<grid, kSkinThreads, 0, st>>>(m.w_idx, m.w_val, m.ell, ws.A + static_cast<size_t>(p0) * kSmplJ * 12,
-                                                    ws.offsets, ws.off_pitch, verts + static_cast<size_t>(p0) * m.V * 3,
-                                                    static_cast<long>(m.V) * 3, m.V, n);
+    const float* Ac = ws.A + static_cast<size_t>(p0) * kSmplJ * 12;
+    float* vc = verts + static_cast<size_t>(p0) * m.V * 3;
+    if (skin_threads == 256) {
+      dim3 grid((m.V + 255) / 256, (n + kSkinPoses - 1) / kSkinPoses);
+      smpl_skin_kernel<256><<<grid, 256, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc,
+                                                  static_cast<long>(m.V) * 3, m.V, n);
+    } else {
+      dim3 grid((m.V + 127) / 128, (n + kSkinPoses - 1) / kSkinPoses);
+      smpl_skin_kernel<128><<<grid, 128, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc,
+                                                  static_cast<long>(m.V) * 3, m.V, n);
+    }
     THMR_CUDA(cudaGetLastError());
   }
   if (joints44) {
@@ -222,7 +232,7 @@ inline size_t engine_build(thmr_engine* e, void* workspace, int B, bool build, i
     d.M = rows; d.N = N; d.K = K;
     d.bias = bias; d.act = act; d.resid = resid; d.ldr = N;
     d.out32 = o32; d.ld32 = N; d.out16 = o16; d.ld16 = N;
-    if (gemm_sk_flag_count(rows, N) <= n_skf) d.sk_flags = skf;
+    if (!c.concurrent && gemm_sk_flag_count(rows, N) <= n_skf) d.sk_flags = skf;   // (stream-K spins across CTA pairs)
     d.a_dead = (A == xn || A == ao || A == hbuf || (A >= xn && A < xn + static_cast<size_t>(M) * D) ||
                 (A >= ao && A < ao + static_cast<size_t>(M) * D) ||
                 (A >= hbuf && A < hbuf + static_cast<size_t>(M) * c.vit_mlp_ratio * D)) ? 1 : 0;

@@ -117,7 +117,7 @@ inline size_t engine_build_strict(thmr_engine* e, void* workspace, int B, bool b
     d.alpha = kStrictAlpha;
     if (a.taps > 1) { d.taps = a.taps; d.cin = 3 * a.K; d.tap_row0 = -a.dil; d.tap_stride = a.dil; }
     d.seq_pitch = a.seq_pitch; d.seq_lo = a.seq_lo; d.seq_hi = a.seq_hi;
-    if (gemm_sk_flag_count(a.rows, a.N) <= n_skf) d.sk_flags = skf;
+    if (!c.concurrent && gemm_sk_flag_count(a.rows, a.N) <= n_skf) d.sk_flags = skf;
     GemmPlan plan;
     const int s = gemm_make_plan(d, &plan);
     if (s != THMR_OK) { err = s; return; }

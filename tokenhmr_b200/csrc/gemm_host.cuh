@@ -32,6 +32,10 @@ struct GemmDesc {
   int seq_pitch = 0, seq_lo = 0, seq_hi = 0;
   float alpha = 1.0f;
   long long* argmin_out = nullptr; const float* row_sq = nullptr; const float* col_sq = nullptr;
+  // screened arg-min (GemmParams): pass 1 queues uncertain rows, the exact pass takes its row count from the device
+  int* screen_rows = nullptr; int* screen_count = nullptr; const float* screen_cmax2 = nullptr;
+  float screen_rel = 0.f, screen_abs = 0.f; int screen_row0 = 0;
+  const int* row_map = nullptr; const int* m_dev = nullptr; int m_dev_off = 0;
   int force_bn = 0;
   int force_epi = -1;  // 0 forces the generic epilogue (tests)
   int force_2cta = -1; // -1 auto, 0 never, 1 always (when eligible)
@@ -119,6 +123,12 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   { const char* e = getenv("THMR_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("THMR_GEMM_COUNTERS"); p.dbg_counters = e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   p.alpha = d.alpha; p.argmin_out = d.argmin_out; p.row_sq = d.row_sq; p.col_sq = d.col_sq;
+  THMR_CHECK(!d.screen_rows || (d.argmin_out && d.screen_count && d.screen_cmax2 && d.N % 32 == 0),
+             "gemm: screened arg-min needs its queue and N %% 32 == 0");
+  THMR_CHECK((!d.m_dev && !d.row_map) || d.argmin_out, "gemm: device row count / row map are arg-min options");
+  p.screen_rows = d.screen_rows; p.screen_count = d.screen_count; p.screen_cmax2 = d.screen_cmax2;
+  p.screen_rel = d.screen_rel; p.screen_abs = d.screen_abs; p.screen_row0 = d.screen_row0;
+  p.row_map = d.row_map; p.m_dev = d.m_dev; p.m_dev_off = d.m_dev_off;
   // THMR_L2_HINTS bits: 1 = dead A operands evict_first, 2 = attention Q/K/V evict_first, 4 = reduce-add target evict_last
   static const int env_hints = [] { const char* e = getenv("THMR_L2_HINTS"); return e ? atoi(e) : 0; }();
   p.l2_hints = ((env_hints & 1) && d.a_dead ? 1 : 0) | (env_hints & 4);

@@ -50,6 +50,20 @@ struct GemmParams {
   long long* argmin_out;   // [M] int64 (nullable = normal GEMM)
   const float* row_sq;     // [M]
   const float* col_sq;     // [N]
+  // screened row-argmin (vq.cuh, two-pass hard quantise).  Pass 1 (screen_rows != nullptr) runs single-product fp16
+  // operands, keeps the best AND the second-best of  e = col_sq - 2*alpha*acc  per row, always stores the best index
+  // and appends the row to screen_rows when (second - best) does not exceed the rigorous error margin
+  //   tau = screen_rel * sqrt(row_sq * cmax2) + screen_abs * (row_sq + cmax2) + 1e-12   (cmax2 = max col_sq);
+  // such rows are re-done by the exact split-precision pass.  The exact pass reads its row count from device memory
+  // (m_dev, minus m_dev_off, clamped to [0, M]) and scatters through row_map.
+  int* screen_rows;            // [>= M rows of capacity overall] global row ids of the rows to re-do (nullable)
+  int* screen_count;           // device counter (appended with one atomicAdd per warp)
+  const float* screen_cmax2;   // device scalar: max over col_sq
+  float screen_rel, screen_abs;
+  int screen_row0;             // global id of row 0 of this launch (pass 1 runs in L2-sized chunks)
+  const int* row_map;          // exact pass: argmin_out[row_map[row]] (nullable = identity)
+  const int* m_dev;            // device row count (nullable = M)
+  int m_dev_off;
   // stream-K (CTA-pair kernel, reduce-add epilogue): non-null = the k-blocks of all tiles are cut into one contiguous
   // range per cluster; a tile shared by two clusters is reduce-added in a FIXED order through these flags
   // ([tile][cta rank][column half], zero between launches)
@@ -103,7 +117,7 @@ struct GemmSmem {
   static constexpr uint32_t kStagingOffset = STAGES * kStageBytes;              // 1024-aligned
   static constexpr uint32_t kStagingBytes = (EPI == kEpiGeneric) ? 0 : kGemmEpiWarps * 4096;
   static constexpr uint32_t kBarOffset = kStagingOffset + kStagingBytes;
-  static constexpr uint32_t kTotal = kBarOffset + 1280 + 1024;  // barriers + argmin exchange, alignment slack
+  static constexpr uint32_t kTotal = kBarOffset + 1792 + 1024;  // barriers + argmin exchange, alignment slack
 };
 
 // Exact-erf GELU (nn.GELU default, vit.py:73).  The epilogue evaluates 63 M of these per MLP layer, so erf uses
@@ -186,11 +200,19 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* xch_val = reinterpret_cast<float*>(smem + S::kBarOffset + 256);   // [128] argmin exchange
   int* xch_idx = reinterpret_cast<int*>(xch_val + 128);                     // [128]
+  float* xch_sec = reinterpret_cast<float*>(xch_idx + 128);                 // [128] second-best (screened arg-min)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (p.M + kGemmBM - 1) / kGemmBM;
+  // rows of this launch: p.M, or (exact pass of the screened arg-min) a count a previous kernel left in device memory.
+  // Every thread reads the same word, so the three warp roles walk identical tile sequences.
+  int M_eff = p.M;
+  if (p.m_dev != nullptr) {
+    const int m = __ldg(p.m_dev) - p.m_dev_off;
+    M_eff = m < 0 ? 0 : (m < p.M ? m : p.M);
+  }
+  const int tiles_m = (M_eff + kGemmBM - 1) / kGemmBM;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
@@ -321,11 +343,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool vec32 = (!p.out32 || p.ld32 % 4 == 0) && (!p.resid || p.ldr % 4 == 0);
       float best = INFINITY;
       int best_idx = 0;
+      float second = INFINITY;                 // screened arg-min: second-smallest value of the row
+      const bool screen = p.argmin_out != nullptr && p.screen_rows != nullptr;
+      const float m2a = -2.0f * p.alpha;
       for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
         const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
+        const bool row_ok = row < M_eff;
         bool row_zero = false;
         if (p.seq_pitch > 0) {
           const int r = row % p.seq_pitch;
@@ -354,7 +379,26 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tmem_ld_x32(tmem_base + lane_addr + acc * BN + c * 32, v);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
-          if (p.argmin_out) {
+          if (screen) {
+            // pass 1 of the screened arg-min: e = col_sq - 2 alpha acc (the row norm is common to every column), running
+            // best / second best; ties and near-ties are settled by the exact pass, so only the margin matters here
+            if (col0 < p.N) {   // (warp-uniform: shuffles below need every lane; N % 32 == 0 is checked by the host)
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int bl = (cc * 32 + j) >> 2;
+                float c2[4];
+                c2[0] = __shfl_sync(0xffffffffu, cq.x, bl); c2[1] = __shfl_sync(0xffffffffu, cq.y, bl);
+                c2[2] = __shfl_sync(0xffffffffu, cq.z, bl); c2[3] = __shfl_sync(0xffffffffu, cq.w, bl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float d = fmaf(m2a, __uint_as_float(v[j + e]), c2[e]);
+                  second = fminf(second, fmaxf(d, best));
+                  if (d < best) best_idx = col0 + j + e;
+                  best = fminf(best, d);
+                }
+              }
+            }
+          } else if (p.argmin_out) {
             if (col0 < p.N) {   // (warp-uniform: shuffles below need every lane)
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -453,17 +497,37 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (p.argmin_out && it.last_n()) {
           // merge the two column halves: smaller distance wins, equal distances -> smaller index
           // (== first minimum over the whole row, as torch.min returns)
-          if (half == 1) { xch_val[q * 32 + lane] = best; xch_idx[q * 32 + lane] = best_idx; }
+          if (half == 1) {
+            xch_val[q * 32 + lane] = best; xch_idx[q * 32 + lane] = best_idx; xch_sec[q * 32 + lane] = second;
+          }
           named_bar_sync_64(1 + q);
           if (half == 0) {
             const float ob = xch_val[q * 32 + lane];
             const int oi = xch_idx[q * 32 + lane];
+            // second best of the whole row: the smaller of the two seconds and the larger of the two bests
+            const float sec = fminf(fminf(second, xch_sec[q * 32 + lane]), fmaxf(best, ob));
             if (ob < best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
-            if (row_ok) p.argmin_out[row] = best_idx;
+            if (row_ok) p.argmin_out[p.row_map ? __ldg(p.row_map + row) : row] = best_idx;
+            if (screen) {
+              // rows whose margin does not clear the error bound of the single-product pass are queued for the exact pass
+              // (NaNs fail the comparison and are queued too); one atomicAdd per warp
+              const float cm2 = __ldg(p.screen_cmax2);
+              const float tau = p.screen_rel * sqrtf(x2 * cm2) + p.screen_abs * (x2 + cm2) + 1e-12f;
+              const bool redo = row_ok && !(sec - best > tau);
+              const unsigned mask = __ballot_sync(0xffffffffu, redo);
+              if (mask != 0u) {
+                const int leader = __ffs(mask) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(p.screen_count, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (redo) p.screen_rows[base + __popc(mask & ((1u << lane) - 1u))] = p.screen_row0 + row;
+              }
+            }
           }
           named_bar_sync_64(1 + q);
           best = INFINITY;
           best_idx = 0;
+          second = INFINITY;
         }
         // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
         tc_fence_before();
@@ -577,7 +641,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(srow), "r"(pk[7]) : "memory");
           }
           __syncwarp();
-          if (lane == 0 && col0 < p.N && m0 + q * 32 < p.M && !(p.dbg & 2)) {
+          if (lane == 0 && col0 < p.N && m0 + q * 32 < M_eff && !(p.dbg & 2)) {
             if constexpr (EPI == kEpiStore16) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
             else if constexpr (EPI == kEpiStore32) tma_store_2d(&tmC, stage_buf, col0, m0 + q * 32);
             else tma_reduce_add_2d(&tmC, stage_buf, col0, m0 + q * 32);

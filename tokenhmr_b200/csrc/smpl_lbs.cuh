@@ -205,10 +205,15 @@ smpl_pose_kernel(const float* __restrict__ pose, int pose2rot, const float* __re
 // v_posed comes out of the blend GEMM (L2-resident chunk); the next pose's three coordinates are loaded while the current
 // pose is skinned.  The 24 relative transforms of each pose sit in shared memory (odd joint stride: distinct joints
 // hit distinct banks, equal joints broadcast).
+// Launch shape: 256 vertices per block by default.  V = 6890 then gives 27 x ceil(B / 16) blocks, and a 512-pose chunk
+// (864 blocks) is resident all at once (8 blocks of 20 KB / 256 threads per SM = 1184 slots); with 128 vertices per block the
+// same chunk is 1728 blocks on 1628 slots, i.e. a second wave of 100 blocks during which most SMs idle
+// (THMR_SKIN_THREADS=128 selects that shape).
 constexpr int kSkinPoses = 16;
 constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used)
-constexpr int kSkinThreads = 128;
+constexpr int kSkinThreadsDefault = 128;
 
+template <int kSkinThreads>
 __global__ void __launch_bounds__(kSkinThreads)
 smpl_skin_kernel(const int* __restrict__ w_idx, const float* __restrict__ w_val, int ell, const float* __restrict__ A,
                  const float* __restrict__ vposed, long off_pitch, float* __restrict__ verts,

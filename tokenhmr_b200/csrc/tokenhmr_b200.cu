@@ -38,7 +38,7 @@ int dev_clone(T** p, const T* src, size_t n) {
 
 extern "C" {
 
-int thmr_abi_version(void) { return 4; }
+int thmr_abi_version(void) { return 5; }
 
 const char* thmr_last_error(void) { return last_error_buf(); }
 
@@ -112,13 +112,43 @@ int thmr_vit_attention(const void* qkv, int B, int heads, void* out, float* dbg_
 }
 
 // ------------------------------------------------------------------------------------------ VQ
+// Screened (two-pass) arg-min, vq.cuh, for Q >= 8192.  THMR_VQ_SCREEN=0/1 selects the single exact pass / the screened
+// path (read on every call, so that a test can compare the two in one process); both return identical indices.
+constexpr int kVqScreenDefault = 0;
+static bool vq_screen_enabled() {
+  const char* e = getenv("THMR_VQ_SCREEN");
+  return (e ? atoi(e) : kVqScreenDefault) != 0;
+}
+struct VqWs {
+  __half* xs; __half* cs; float* x2; float* c2;                  // exact path / exact pass
+  __half* xh; float* x2f; int* rows; int* count; float* cmax2;   // screened path
+};
+static void vq_carve(Bump& bp, int64_t Q, int K, int D, bool screen, VqWs* w) {
+  memset(w, 0, sizeof(*w));
+  const int64_t cap = screen ? (Q < kVqExactCap ? Q : kVqExactCap) : Q;
+  w->xs = bp.take<__half>(static_cast<size_t>(cap) * 3 * D);
+  w->cs = bp.take<__half>(static_cast<size_t>(K) * 3 * D);
+  w->x2 = bp.take<float>(Q);
+  w->c2 = bp.take<float>(K);
+  if (screen) {
+    w->xh = bp.take<__half>(static_cast<size_t>(Q < kVqScreenChunk ? Q : kVqScreenChunk) * D);
+    w->x2f = bp.take<float>(cap);
+    w->rows = bp.take<int>(Q);
+    w->count = bp.take<int>(4);
+    w->cmax2 = bp.take<float>(4);
+  }
+}
+
 size_t thmr_vq_workspace_bytes(int64_t Q, int K, int D) {
-  Bump bp(nullptr);
-  bp.take<__half>(static_cast<size_t>(Q) * 3 * D);
-  bp.take<__half>(static_cast<size_t>(K) * 3 * D);
-  bp.take<float>(Q);
-  bp.take<float>(K);
-  return (bp.off + 1023) & ~size_t(1023);
+  // the larger of the two layouts, so that the environment switch never invalidates a caller's buffer
+  size_t need = 0;
+  for (int screen = 0; screen < 2; ++screen) {
+    Bump bp(nullptr);
+    VqWs w;
+    vq_carve(bp, Q, K, D, screen != 0, &w);
+    if (bp.off > need) need = bp.off;
+  }
+  return (need + 1023) & ~size_t(1023);
 }
 
 int thmr_vq_argmin(const float* x, int64_t Q, const float* codebook, int K, int D, int64_t* idx, void* workspace,
@@ -127,25 +157,59 @@ int thmr_vq_argmin(const float* x, int64_t Q, const float* codebook, int K, int 
   THMR_CHECK(D % 64 == 0 && Q > 0 && K > 0 && K % 4 == 0 && Q < (1ll << 31), "vq_argmin: unsupported shape Q=%lld K=%d D=%d",
              (long long)Q, K, D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool screen = vq_screen_enabled() && Q >= 8192 && K % 32 == 0;
   Bump bp(workspace);
-  __half* xs = bp.take<__half>(static_cast<size_t>(Q) * 3 * D);
-  __half* cs = bp.take<__half>(static_cast<size_t>(K) * 3 * D);
-  float* x2 = bp.take<float>(Q);
-  float* c2 = bp.take<float>(K);
-  vq_split_rows_kernel<<<static_cast<unsigned>((Q + 7) / 8), 256, 0, st>>>(x, xs, x2, Q, D, 1);
-  THMR_CUDA(cudaGetLastError());
-  vq_split_rows_kernel<<<static_cast<unsigned>((K + 7) / 8), 256, 0, st>>>(codebook, cs, c2, K, D, 0);
+  VqWs w;
+  vq_carve(bp, Q, K, D, screen, &w);
+  vq_split_rows_kernel<<<static_cast<unsigned>((K + 7) / 8), 256, 0, st>>>(codebook, w.cs, w.c2, K, D, 0);
   THMR_CUDA(cudaGetLastError());
   GemmDesc d;
-  d.A = xs; d.lda = 3 * D; d.a_rows = Q;
-  d.B = cs; d.ldb = 3 * D;
-  d.M = static_cast<int>(Q); d.N = K; d.K = 3 * D;
+  d.B = w.cs; d.ldb = 3 * D; d.N = K;
   d.alpha = 1.0f / (kVqScale * kVqScale);
-  d.argmin_out = reinterpret_cast<long long*>(idx); d.row_sq = x2; d.col_sq = c2;
+  d.argmin_out = reinterpret_cast<long long*>(idx); d.col_sq = w.c2;
   d.force_bn = 256;
   GemmPlan plan;
-  THMR_TRY(gemm_make_plan(d, &plan));
-  return gemm_launch(plan, st);
+  if (!screen) {
+    vq_split_rows_kernel<<<static_cast<unsigned>((Q + 7) / 8), 256, 0, st>>>(x, w.xs, w.x2, Q, D, 1);
+    THMR_CUDA(cudaGetLastError());
+    d.A = w.xs; d.lda = 3 * D; d.a_rows = Q;
+    d.M = static_cast<int>(Q); d.K = 3 * D;
+    d.row_sq = w.x2;
+    THMR_TRY(gemm_make_plan(d, &plan));
+    return gemm_launch(plan, st);
+  }
+  // ---- pass 1: one fp16 product per pair (the first D columns of the split codebook are its hi part), L2-sized chunks
+  vq_screen_prep_kernel<<<1, 256, 0, st>>>(w.c2, K, w.cmax2, w.count);
+  THMR_CUDA(cudaGetLastError());
+  for (int64_t q0 = 0; q0 < Q; q0 += kVqScreenChunk) {
+    const int64_t n = (Q - q0) < kVqScreenChunk ? (Q - q0) : kVqScreenChunk;
+    vq_hi_rows_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(x + q0 * D, w.xh, w.x2 + q0, n, D);
+    THMR_CUDA(cudaGetLastError());
+    GemmDesc s = d;
+    s.A = w.xh; s.lda = D; s.a_rows = n;
+    s.M = static_cast<int>(n); s.K = D;
+    s.argmin_out = reinterpret_cast<long long*>(idx) + q0; s.row_sq = w.x2 + q0;
+    s.screen_rows = w.rows; s.screen_count = w.count; s.screen_cmax2 = w.cmax2;
+    s.screen_rel = kVqScreenRel; s.screen_abs = kVqScreenAbs; s.screen_row0 = static_cast<int>(q0);
+    THMR_TRY(gemm_make_plan(s, &plan));
+    THMR_TRY(gemm_launch(plan, st));
+  }
+  // ---- pass 2: the queued rows through the exact split-precision GEMM, kVqExactCap rows per round (the count is only
+  //      known on the device: every round is launched, rounds past the end find zero rows)
+  const int64_t cap = Q < kVqExactCap ? Q : kVqExactCap;
+  for (int64_t off = 0; off < Q; off += cap) {
+    vq_gather_split_kernel<<<num_sms() * 4, 256, 0, st>>>(x, w.rows, w.count, static_cast<int>(off), static_cast<int>(cap),
+                                                         w.xs, w.x2f, D);
+    THMR_CUDA(cudaGetLastError());
+    GemmDesc e = d;
+    e.A = w.xs; e.lda = 3 * D; e.a_rows = cap;
+    e.M = static_cast<int>(cap); e.K = 3 * D;
+    e.row_sq = w.x2f;
+    e.row_map = w.rows + off; e.m_dev = w.count; e.m_dev_off = static_cast<int>(off);
+    THMR_TRY(gemm_make_plan(e, &plan));
+    THMR_TRY(gemm_launch(plan, st));
+  }
+  return THMR_OK;
 }
 
 int thmr_vq_dequantize(const int64_t* idx, int64_t Q, const float* codebook, int D, float* out, void* stream) {

@@ -52,13 +52,17 @@ class _SmplFacade:
 class TokenHMREngine(nn.Module):
     def __init__(self, cfg: TokenHMRConfig, state_dict: Dict[str, torch.Tensor], smpl: Dict[str, torch.Tensor],
                  device: str | torch.device = "cuda:0", max_batch: int = 256, use_cuda_graph: bool = True,
-                 strict: bool = False, alias_outputs: bool = False, max_cached_shapes: int = 6):
+                 strict: bool = False, alias_outputs: bool = False, max_cached_shapes: int = 6,
+                 concurrent: bool = False):
         """strict: every contraction of the path in split-fp16 (3 tensor-core products, ~2^-21 relative: fp32-grade)
         instead of fp16 operands -- the mode whose results match the fp32 reference to 1e-4 with identical pose tokens
         (DESIGN.md §2); about 4x slower.  alias_outputs: return views of the engine's static output buffers (valid until
         the next forward of the same batch size / slot) instead of fresh tensors; TokenHMRPipeline uses it.
         max_batch: largest batch a forward accepts (bounds the workspace).  max_cached_shapes: distinct (batch size, slot)
-        buffer sets kept alive; the least recently used one is dropped beyond that."""
+        buffer sets kept alive; the least recently used one is dropped beyond that.
+        concurrent: the forwards of different slots may run at the same time on different streams
+        (TokenHMRPipeline(streams=2)); the engine then avoids kernels that need the whole GPU to themselves
+        (thmr_config::concurrent)."""
         super().__init__()
         self.cfg = cfg
         self.device = torch.device(device)
@@ -70,13 +74,14 @@ class TokenHMREngine(nn.Module):
         from .checkpoint import validate_against_weights
         validate_against_weights(cfg, state_dict, smpl)
         self.strict = bool(strict)
+        self.concurrent = bool(concurrent)
         self.alias_outputs = bool(alias_outputs)
         self.max_cached_shapes = int(max_cached_shapes)
         with torch.cuda.device(self.device):
             self.weights = PackedWeights(state_dict, cfg, self.device, strict=self.strict)
             self.smpl_model = SMPLModel(smpl, self.device)
             self.smpl = _SmplFacade(self.smpl_model)
-            self._cfg_struct = make_config_struct(cfg, strict=self.strict)
+            self._cfg_struct = make_config_struct(cfg, strict=self.strict, concurrent=self.concurrent)
             h = ctypes.c_void_p()
             check(lib().thmr_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self.weights.struct),
                                            self.smpl_model.handle, ctypes.byref(h)))
@@ -325,19 +330,32 @@ class TokenHMRPipeline:
 
     Nothing is skipped: every submit copies its own input and every result is read back; only the waiting is moved, so
     the copy engines work while the SMs run the previous batch.  `post(out)` (optional) runs on the compute stream between
-    the forward and the read-back (e.g. the all-gather of a sharded model)."""
+    the forward and the read-back (e.g. the all-gather of a sharded model).
+
+    streams=2 additionally lets the forwards of consecutive batches overlap on the SMs: slot s replays its CUDA graph
+    on compute stream s % streams, so the latency-bound tail of batch i (token decoder, classifier, tokenizer decoder,
+    SMPL: ~80 small launches that leave most SMs idle) runs under the ViT GEMMs of batch i+1.  Needs an engine built
+    with concurrent=True; single-GPU only (the sharded forward's in-graph collective keeps one stream)."""
 
     def __init__(self, model: "TokenHMREngine", depth: int = 2, read_back=("pred_vertices", "pred_keypoints_3d",
                                                                          "pred_cam", "pred_cam_t"), post=None,
-                 shard: Optional[ShardSpec] = None, read_rows: Optional[slice] = None):
+                 shard: Optional[ShardSpec] = None, read_rows: Optional[slice] = None, streams: int = 1):
         """shard: run every forward as this rank's part of a sharded batch (in-place all-gather inside the forward's CUDA
         graph).  read_rows: rows of each output to copy back to the host (e.g. only this rank's own images when the
         ranks of one host each hand their shard to the same consumer); default all rows."""
         self.model, self.depth, self.read_back, self.post = model, int(depth), tuple(read_back), post
         self.shard, self.read_rows = shard, read_rows
+        self.streams = int(streams)
+        if not 1 <= self.streams <= self.depth:
+            raise _lib.ThmrError(f"TokenHMRPipeline: streams={streams} must be in [1, depth={depth}]")
+        if self.streams > 1 and not getattr(model, "concurrent", False):
+            raise _lib.ThmrError("TokenHMRPipeline(streams > 1) needs TokenHMREngine(concurrent=True)")
+        if self.streams > 1 and shard is not None and shard.world > 1:
+            raise _lib.ThmrError("TokenHMRPipeline(streams > 1): the sharded forward (in-graph collective) keeps one stream")
         with torch.cuda.device(model.device):
             self.copy_stream = torch.cuda.Stream(model.device)
-            self.compute_stream = torch.cuda.Stream(model.device)
+            self.compute_streams = [torch.cuda.Stream(model.device) for _ in range(self.streams)]
+            self.compute_stream = self.compute_streams[0]
             self._copied = [torch.cuda.Event() for _ in range(self.depth)]
             self._done = [torch.cuda.Event() for _ in range(self.depth)]
         self._used = [False] * self.depth
@@ -358,8 +376,9 @@ class TokenHMRPipeline:
                     self.copy_stream.wait_event(self._done[slot])       # the slot's previous forward has consumed its input
                 st["t"]["img"].copy_(img, non_blocking=True)
                 self._copied[slot].record(self.copy_stream)
-            with torch.cuda.stream(self.compute_stream):
-                self.compute_stream.wait_event(self._copied[slot])
+            cs = self.compute_streams[slot % self.streams]
+            with torch.cuda.stream(cs):
+                cs.wait_event(self._copied[slot])
                 out = m.forward({"img": st["t"]["img"]}, slot=slot, alias_outputs=True,   # (input self-copy: a no-op)
                                 shard=self.shard)
                 if self.post is not None:
@@ -370,9 +389,17 @@ class TokenHMRPipeline:
                     if k not in host or host[k].shape != src.shape:
                         host[k] = torch.empty(src.shape, dtype=src.dtype).pin_memory()
                     host[k].copy_(src, non_blocking=True)
-                self._done[slot].record(self.compute_stream)
+                self._done[slot].record(cs)
             self._used[slot] = True
         return ticket
+
+    def join(self) -> "torch.cuda.Stream":
+        """compute_stream after it has been made to wait for every submitted batch (all slots, all streams): the place
+        to record an end-of-work event."""
+        for used, ev in zip(self._used, self._done):
+            if used:
+                self.compute_stream.wait_event(ev)
+        return self.compute_stream
 
     def result(self, ticket: int) -> Dict[str, torch.Tensor]:
         slot = ticket % self.depth

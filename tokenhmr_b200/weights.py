@@ -167,9 +167,10 @@ class PackedWeights:
         return sum(t.numel() * t.element_size() for t in self._keep)
 
 
-def make_config_struct(cfg: TokenHMRConfig, strict: bool = False) -> _lib.Config:
+def make_config_struct(cfg: TokenHMRConfig, strict: bool = False, concurrent: bool = False) -> _lib.Config:
     c = _lib.Config()
     c.strict = 1 if strict else 0
+    c.concurrent = 1 if concurrent else 0
     for f in ("image_size", "crop_w", "patch", "patch_pad", "vit_dim", "vit_depth", "vit_heads", "vit_mlp_ratio",
               "vit_ln_eps", "dec_dim", "dec_depth", "dec_heads", "dec_dim_head", "dec_mlp_dim", "ln_eps", "token_num",
               "token_class_num", "cls_hidden", "cls_hidden_inter", "cls_token_inter", "cls_blocks", "code_dim",
