@@ -393,6 +393,8 @@ def main():
     # concurrent=True (no stream-K fc2: its CTA pairs spin on each other and must own the GPU).
     dual, model2 = None, None
     want_dual = world == 1 and args.streams in (0, 2)
+    if rank == 0:
+        print(json.dumps({"early": "one-stream replay", "value": value, "ms_per_step": ms_step}), file=sys.stderr, flush=True)
     if want_dual:
         model2 = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, concurrent=True)
         s2 = [torch.cuda.Stream(dev) for _ in range(2)]
@@ -426,6 +428,9 @@ def main():
         dual = {"value": B * 1e3 / ms_dual, "ms_per_step": ms_dual, "streams": 2, "window": (t_d0, t_d1),
                 "max_abs_vertex_diff_vs_serial": dev_max,
                 "what": "step i replays slot i%2's graph on stream i%2 (TokenHMREngine(concurrent=True)); ms_per_step = region / K"}
+        if rank == 0:
+            print(json.dumps({"early": "two-stream replay", "value": dual["value"], "ms_per_step": ms_dual,
+                              "max_abs_vertex_diff_vs_serial": dev_max}), file=sys.stderr, flush=True)
     head = dual if (dual is not None and (args.streams == 2 or dual["value"] > serial["value"])) else serial
     value, ms_step_head = head["value"], head["ms_per_step"]
     clocks = None

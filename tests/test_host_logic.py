@@ -83,3 +83,51 @@ def test_split_weight_layout_and_precision():
     import pytest
     with pytest.raises(ThmrError):
         split_weight(torch.full((2, 4), 300.0))
+
+
+def _vq_screen_constants():
+    """kVqScale / kVqScreenRel / kVqScreenAbs as compiled into the library (parsed from csrc/vq.cuh so that the
+    emulation below cannot drift from the kernel)."""
+    import re
+    from pathlib import Path
+    src = (Path(__file__).resolve().parent.parent / "tokenhmr_b200" / "csrc" / "vq.cuh").read_text()
+    scale = float(re.search(r"kVqScale = ([0-9.]+)f", src).group(1))
+    m = re.search(r"kVqScreenRel = ([0-9.]+)f \* ([0-9.]+)f", src)
+    rel = float(m.group(1)) * float(m.group(2))
+    ab = float(re.search(r"kVqScreenAbs = ([0-9.e+-]+)f", src).group(1))
+    return scale, rel, ab
+
+
+def test_vq_screen_margin_is_sound_numpy_emulation():
+    """Emulates pass 1 of the screened arg-min (csrc/vq.cuh, gemm_tcgen05.cuh) in numpy: fp16-rounded operands, fp32
+    accumulation, best / second best of e = |c|^2 - 2 x.c, margin tau.  Soundness: every row that pass 1 would NOT hand to the
+    exact pass already has the fp64 arg-min.  Also: the error of the single-product e stays inside the bound eps = tau / 2
+    the margin is built from, and the share of re-done rows is what DESIGN.md quotes (about a tenth of N(0,1) queries)."""
+    import numpy as np
+    scale, rel, ab = _vq_screen_constants()
+    assert abs(rel - 2.0 ** -8 * 1.05) < 1e-9
+    rng = np.random.default_rng(5)
+    for xs, cs in ((1.0, 1.0), (6.0, 0.2), (1e-2, 3.0)):
+        C = (cs * rng.standard_normal((2048, 256))).astype(np.float32)
+        X = (xs * rng.standard_normal((3000, 256))).astype(np.float32)
+        # near-ties on purpose: midpoints of two codes (+ a little noise)
+        a, b = rng.integers(0, 2048, 300), rng.integers(0, 2048, 300)
+        X[:300] = 0.5 * (C[a] + C[b]) + (1e-4 * cs * rng.standard_normal((300, 256))).astype(np.float32)
+        c2 = (C.astype(np.float64) ** 2).sum(1)
+        x2 = (X.astype(np.float64) ** 2).sum(1)
+        exact = c2[None, :] - 2.0 * (X.astype(np.float64) @ C.astype(np.float64).T)
+        Xh = (X * scale).astype(np.float16).astype(np.float32)
+        Ch = (C * scale).astype(np.float16).astype(np.float32)
+        acc = Xh @ Ch.T                                             # fp32 accumulate of exact fp16 x fp16 products
+        e = (np.float32(-2.0 / (scale * scale)) * acc + c2.astype(np.float32)[None, :]).astype(np.float32)
+        order = np.argsort(e, axis=1, kind="stable")
+        best, second = e[np.arange(len(e)), order[:, 0]], e[np.arange(len(e)), order[:, 1]]
+        cmax2 = np.float32(c2.max())
+        tau = (np.float32(rel) * np.sqrt(x2.astype(np.float32) * cmax2) + np.float32(ab) * (x2.astype(np.float32) + cmax2)
+               + np.float32(1e-12))
+        redo = ~((second - best) > tau)
+        final = ~redo
+        assert np.array_equal(order[final, 0], exact.argmin(1)[final])
+        assert (np.abs(e - exact).max(1) <= 0.5 * tau).all()        # the bound the margin is built from
+        assert redo[:300].mean() > 0.9                               # planted near-ties are re-done
+        assert redo[300:].mean() < 0.3, redo[300:].mean()

@@ -211,7 +211,7 @@ smpl_pose_kernel(const float* __restrict__ pose, int pose2rot, const float* __re
 // (THMR_SKIN_THREADS=128 selects that shape).
 constexpr int kSkinPoses = 16;
 constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used)
-constexpr int kSkinThreadsDefault = 128;
+constexpr int kSkinThreadsDefault = 256;
 
 template <int kSkinThreads>
 __global__ void __launch_bounds__(kSkinThreads)

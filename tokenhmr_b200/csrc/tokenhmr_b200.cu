@@ -114,7 +114,7 @@ int thmr_vit_attention(const void* qkv, int B, int heads, void* out, float* dbg_
 // ------------------------------------------------------------------------------------------ VQ
 // Screened (two-pass) arg-min, vq.cuh, for Q >= 8192.  THMR_VQ_SCREEN=0/1 selects the single exact pass / the screened
 // path (read on every call, so that a test can compare the two in one process); both return identical indices.
-constexpr int kVqScreenDefault = 0;
+constexpr int kVqScreenDefault = 1;
 static bool vq_screen_enabled() {
   const char* e = getenv("THMR_VQ_SCREEN");
   return (e ? atoi(e) : kVqScreenDefault) != 0;
