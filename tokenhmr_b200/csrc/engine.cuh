@@ -91,15 +91,16 @@ inline int smpl_run(const thmr_smpl* sm, const float* pose, int pose2rot, const 
     THMR_TRY(gemm_launch(*plan, st));
     const float* Ac = ws.A + static_cast<size_t>(p0) * kSmplJ * 12;
     float* vc = verts + static_cast<size_t>(p0) * m.V * 3;
-    if (skin_threads == 256) {
-      dim3 grid((m.V + 255) / 256, (n + kSkinPoses - 1) / kSkinPoses);
-      smpl_skin_kernel<256><<<grid, 256, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc,
-                                                  static_cast<long>(m.V) * 3, m.V, n);
-    } else {
-      dim3 grid((m.V + 127) / 128, (n + kSkinPoses - 1) / kSkinPoses);
-      smpl_skin_kernel<128><<<grid, 128, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc,
-                                                  static_cast<long>(m.V) * 3, m.V, n);
-    }
+    const dim3 grid((m.V + skin_threads - 1) / skin_threads, (n + kSkinPoses - 1) / kSkinPoses);
+    const long vp = static_cast<long>(m.V) * 3;
+    if (skin_threads == 256 && m.ell <= 4)
+      smpl_skin_kernel<256, 4><<<grid, 256, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc, vp, m.V, n);
+    else if (skin_threads == 256)
+      smpl_skin_kernel<256, 8><<<grid, 256, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc, vp, m.V, n);
+    else if (m.ell <= 4)
+      smpl_skin_kernel<128, 4><<<grid, 128, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc, vp, m.V, n);
+    else
+      smpl_skin_kernel<128, 8><<<grid, 128, 0, st>>>(m.w_idx, m.w_val, m.ell, Ac, ws.offsets, ws.off_pitch, vc, vp, m.V, n);
     THMR_CUDA(cudaGetLastError());
   }
   if (joints44) {

@@ -213,8 +213,10 @@ constexpr int kSkinPoses = 16;
 constexpr int kSkinAStride = 13;   // floats per joint in smem (12 used)
 constexpr int kSkinThreadsDefault = 256;
 
-template <int kSkinThreads>
-__global__ void __launch_bounds__(kSkinThreads)
+// kEllReg: skinning weights held in registers (4 for SMPL's 4 influences per vertex: 40 registers per thread, so that six
+// 256-thread blocks = 888 block slots fit an SM and the 864 blocks of a chunk form ONE wave; 8 otherwise).
+template <int kSkinThreads, int kEllReg>
+__global__ void __launch_bounds__(kSkinThreads, (kSkinThreads == 256) ? (kEllReg == 4 ? 6 : 4) : 10)
 smpl_skin_kernel(const int* __restrict__ w_idx, const float* __restrict__ w_val, int ell, const float* __restrict__ A,
                  const float* __restrict__ vposed, long off_pitch, float* __restrict__ verts,
                  long vert_pitch /* floats between poses */, int V, int B) {
@@ -229,7 +231,6 @@ smpl_skin_kernel(const int* __restrict__ w_idx, const float* __restrict__ w_val,
   const int v = blockIdx.x * kSkinThreads + threadIdx.x;
   if (v >= V) return;
   // skinning weights of this vertex: registers when the ELL width is small (real SMPL: 4), else re-read
-  constexpr int kEllReg = 8;
   int wi[kEllReg];
   float wv[kEllReg];
 #pragma unroll
