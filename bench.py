@@ -309,9 +309,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone configs and the strict-mode rate")
-    ap.add_argument("--streams", type=int, default=0, choices=[0, 1, 2],
-                    help="1: consecutive steps replay on one stream; 2: on two streams (the tail of step i overlaps the ViT of "
-                         "step i+1, single GPU only); 0 (default): measure both at N=1 and report the faster as `value`")
+    ap.add_argument("--streams", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="1: consecutive steps replay on one stream; n > 1: round-robin on n streams (n steps in flight, single "
+                         "GPU only); 0 (default): measure 1 and 4 at N=1 and report the faster as `value`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -386,30 +386,33 @@ def main():
     value = world * B * 1e3 / ms_step
     serial = {"value": value, "ms_per_step": ms_step, "streams": 1, "window": (t_win0, t_win1)}
 
-    # ---- (1b) the same K steps on TWO streams (single GPU): step i replays slot i%2's CUDA graph on stream i%2, so the
-    # latency-bound tail of one step (decoder / classifier / tokenizer decoder / SMPL: ~80 small launches on a mostly idle
-    # GPU) runs under the ViT GEMMs of the next.  Every step is still a complete bs=64 forward with its own buffers; the
-    # region is timed from an event both streams wait for to an event that waits for both.  The engine is built with
-    # concurrent=True (no stream-K fc2: its CTA pairs spin on each other and must own the GPU).
+    # ---- (1b) the same K steps round-robin on n streams (single GPU): step i replays slot i%n's CUDA graph on stream i%n,
+    # so whenever the kernel one step is running leaves SMs idle (the last wave of a persistent GEMM, the ~80 small launches
+    # of the decoder / classifier / tokenizer-decoder / SMPL tail) the block scheduler fills them with another step's next
+    # kernel.  Every step is still a complete bs=64 forward with its own buffers; the region is timed from an event all
+    # streams wait for to an event that waits for all of them.  The engine is built with concurrent=True (no stream-K fc2:
+    # its CTA pairs spin on each other and must own the GPU).  Measured (scripts/dev_streams.py): 1 / 2 / 3 / 4 streams =
+    # 17.99 / 17.21 / 17.23 / 17.07 ms per step (17.72 for the default engine with stream-K on one stream).
     dual, model2 = None, None
-    want_dual = world == 1 and args.streams in (0, 2)
+    want_dual = world == 1 and args.streams != 1
+    NS = args.streams if args.streams > 1 else 4
     if rank == 0:
         print(json.dumps({"early": "one-stream replay", "value": value, "ms_per_step": ms_step}), file=sys.stderr, flush=True)
     if want_dual:
-        model2 = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, concurrent=True)
-        s2 = [torch.cuda.Stream(dev) for _ in range(2)]
-        last = [None, None]
+        model2 = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, concurrent=True, max_cached_shapes=8)
+        s2 = [torch.cuda.Stream(dev) for _ in range(NS)]
+        last = [None] * NS
 
         def step_dual(i):
-            with torch.cuda.stream(s2[i & 1]):
-                last[i & 1] = model2.forward({"img": img_dev}, alias_outputs=True, slot=i & 1)
+            with torch.cuda.stream(s2[i % NS]):
+                last[i % NS] = model2.forward({"img": img_dev}, alias_outputs=True, slot=i % NS)
 
-        for i in range(max(args.warmup, 4)):
+        for i in range(max(args.warmup, 2 * NS)):
             step_dual(i)
         torch.cuda.synchronize()
         ref_v = step_resident()["pred_vertices"]
         torch.cuda.synchronize()
-        dev_max = max(float((last[s]["pred_vertices"] - ref_v).abs().max()) for s in range(2))
+        dev_max = max(float((last[s]["pred_vertices"] - ref_v).abs().max()) for s in range(NS))
         main = torch.cuda.current_stream()
         t_d0 = time.time()
         e0.record(main)
@@ -425,13 +428,14 @@ def main():
         torch.cuda.synchronize()
         t_d1 = time.time()
         ms_dual = e0.elapsed_time(e1) / args.steps
-        dual = {"value": B * 1e3 / ms_dual, "ms_per_step": ms_dual, "streams": 2, "window": (t_d0, t_d1),
+        dual = {"value": B * 1e3 / ms_dual, "ms_per_step": ms_dual, "streams": NS, "window": (t_d0, t_d1),
                 "max_abs_vertex_diff_vs_serial": dev_max,
-                "what": "step i replays slot i%2's graph on stream i%2 (TokenHMREngine(concurrent=True)); ms_per_step = region / K"}
+                "what": f"step i replays slot i%{NS}'s graph on stream i%{NS} (TokenHMREngine(concurrent=True)); "
+                        "ms_per_step = region / K (the latency of one step is about n times that)"}
         if rank == 0:
-            print(json.dumps({"early": "two-stream replay", "value": dual["value"], "ms_per_step": ms_dual,
+            print(json.dumps({"early": f"{NS}-stream replay", "value": dual["value"], "ms_per_step": ms_dual,
                               "max_abs_vertex_diff_vs_serial": dev_max}), file=sys.stderr, flush=True)
-    head = dual if (dual is not None and (args.streams == 2 or dual["value"] > serial["value"])) else serial
+    head = dual if (dual is not None and (args.streams > 1 or dual["value"] > serial["value"])) else serial
     value, ms_step_head = head["value"], head["ms_per_step"]
     clocks = None
     if rank == 0:
@@ -454,13 +458,17 @@ def main():
     pipe = TokenHMRPipeline(model, depth=2, read_back=consumed, shard=spec, read_rows=rows)
 
     def run_e2e(n):
-        pending = None
+        """n batches through the pipeline, pipe.depth of them in flight; every batch's results are waited for on the host."""
+        tickets, done, out = [], 0, None
         for _ in range(n):
-            t = pipe.submit({"img": img_host})
-            if pending is not None:
-                pipe.result(pending)
-            pending = t
-        return pipe.result(pending)
+            tickets.append(pipe.submit({"img": img_host}))
+            if len(tickets) - done >= pipe.depth:
+                out = pipe.result(tickets[done])
+                done += 1
+        while done < len(tickets):
+            out = pipe.result(tickets[done])
+            done += 1
+        return out
 
     run_e2e(4)                       # builds both slots (plans, graphs, pinned result buffers)
     barrier()
@@ -473,18 +481,18 @@ def main():
     e2e_modes = {"streams_1": {"value": e2e_value, "ms_per_step": ms_e2e}}
     e2e_streams = 1
     if want_dual:
-        pipe1, pipe = pipe, TokenHMRPipeline(model2, depth=2, read_back=consumed, streams=2)
-        run_e2e(4)
+        pipe1, pipe = pipe, TokenHMRPipeline(model2, depth=NS, read_back=consumed, streams=NS)
+        run_e2e(2 * NS)
         torch.cuda.synchronize()
         e0.record(pipe.copy_stream)
         host_out2 = run_e2e(args.steps)
         e1.record(pipe.join())
         torch.cuda.synchronize()
         ms2 = e0.elapsed_time(e1) / args.steps
-        e2e_modes["streams_2"] = {"value": B * 1e3 / ms2, "ms_per_step": ms2,
+        e2e_modes["streams_n"] = {"value": B * 1e3 / ms2, "ms_per_step": ms2, "streams": NS, "depth": NS,
                                   "max_abs_vertex_diff_vs_streams_1": float((host_out2["pred_vertices"] - host_out["pred_vertices"]).abs().max())}
-        if args.streams == 2 or B * 1e3 / ms2 > e2e_value:
-            e2e_value, ms_e2e, e2e_streams = B * 1e3 / ms2, ms2, 2
+        if args.streams > 1 or B * 1e3 / ms2 > e2e_value:
+            e2e_value, ms_e2e, e2e_streams = B * 1e3 / ms2, ms2, NS
         del pipe1
     h2d = img_host.numel() * 4
     d2h = sum(v.numel() * 4 for v in host_out.values())
@@ -572,11 +580,12 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step_head, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": dict(workload_config(world), streams=head["streams"]),
-            "streams_1": serial, "streams_2": dual,
+            "streams_1": serial, "streams_n": dual,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "read_back": consumed, "streams": e2e_streams, "modes": e2e_modes,
-                    "api": "TokenHMRPipeline.submit/result (depth 2: H2D of the next batch overlaps the forward"
-                           + ("; streams=2: consecutive forwards overlap too)" if e2e_streams == 2 else ")")
+                    "api": (f"TokenHMRPipeline.submit/result (depth {e2e_streams}, streams {e2e_streams}: {e2e_streams} batches in "
+                            "flight, H2D / forward / D2H of different batches overlap)" if e2e_streams > 1 else
+                            "TokenHMRPipeline.submit/result (depth 2: H2D of the next batch overlaps the forward)")
                            + ("; each rank reads back its own shard" if world > 1 else "")},
             "gpu_launches": args.steps * launches, "launches_per_step": launches,
             "exchange": (None if world == 1 else "thmr_allgather_outputs: 8 grouped in-place ncclAllGather (one NCCL kernel) "

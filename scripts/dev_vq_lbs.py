@@ -12,8 +12,12 @@ def ev(fn, n=5):
     return e0.elapsed_time(e1) / n
 if "vq" in what:
     cb = torch.randn(2048, 256, device=dev); x = torch.randn(1_000_000, 256, device=dev)
-    ms = ev(lambda: ops.vq_quantize(x, cb))
-    print(f"vq 1M: {ms:.2f} ms  {1e3/ms:.0f} Mq/s  ({3*2*1e6*2048*256/ms/1e9:.0f} TFLOP/s split-precision, {2*1e6*2048*256/ms/1e9:.0f} algorithmic)")
+    import os
+    for mode in ("1", "0"):
+        os.environ["THMR_VQ_SCREEN"] = mode
+        ms = ev(lambda: ops.vq_quantize(x, cb))
+        print(f"vq 1M ({'screened' if mode == '1' else 'exact'}): {ms:.2f} ms  {1e3/ms:.0f} Mq/s  ({2*1e6*2048*256/ms/1e9:.0f} TFLOP/s algorithmic)")
+    os.environ.pop("THMR_VQ_SCREEN")
     pick = torch.randint(0, 2048, (100000,), device=dev)
     xn = cb[pick] + 0.05 * torch.randn(100000, 256, device=dev)
     print("vq near-code exact:", torch.equal(ops.vq_quantize(xn, cb), pick))

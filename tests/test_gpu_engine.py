@@ -184,7 +184,7 @@ def test_two_stream_pipeline_matches_synchronous_forward(cuda_dev):
     from tokenhmr_b200.engine import TokenHMREngine, TokenHMRPipeline
     cfg = tiny_config(vit_depth=2)
     sd, smpl = synth.make_state_dict(cfg), synth.make_smpl(cfg)
-    model = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=False, concurrent=True)
+    model = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=False, concurrent=True, max_cached_shapes=8)
     keys = ("pred_vertices", "pred_keypoints_3d", "pred_cam", "pred_cam_t")
     batches = [synth.make_images(8, cfg, seed=60 + i).pin_memory() for i in range(9)]
     want = []
@@ -192,8 +192,8 @@ def test_two_stream_pipeline_matches_synchronous_forward(cuda_dev):
         out = model({"img": b})
         want.append({k: out[k].cpu().clone() for k in keys})
     model.use_cuda_graph = True
-    for depth in (2, 3):
-        pipe = TokenHMRPipeline(model, depth=depth, read_back=keys, streams=2)
+    for depth, streams in ((2, 2), (4, 2), (4, 4)):
+        pipe = TokenHMRPipeline(model, depth=depth, read_back=keys, streams=streams)
         tickets = []
         got = []
         for b in batches:
@@ -204,7 +204,7 @@ def test_two_stream_pipeline_matches_synchronous_forward(cuda_dev):
             got.append({k: v.clone() for k, v in pipe.result(tickets[len(got)]).items()})
         for g, w in zip(got, want):
             for k in keys:
-                assert torch.equal(g[k], w[k]), (depth, k)
+                assert torch.equal(g[k], w[k]), (depth, streams, k)
     plain = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=True)
     with pytest.raises(_lib.ThmrError):
         TokenHMRPipeline(plain, depth=2, streams=2)

@@ -205,6 +205,9 @@ inline int gemm_make_plan(const GemmDesc& d, GemmPlan* plan) {
   }
   const long tiles_m = (d.M + kGemmBM - 1) / kGemmBM;
   const long tiles = d.argmin_out ? tiles_m : tiles_m * ((d.N + bn - 1) / bn);
+  // the CTAs of a wave should share tiles of the larger operand (TileIter); THMR_GEMM_MFAST=0 keeps column-fastest order
+  static const int env_mfast = [] { const char* e = getenv("THMR_GEMM_MFAST"); return e ? atoi(e) : 1; }();
+  p.m_fast = (env_mfast && !d.argmin_out && tiles_m > 1 && d.M < d.N) ? 1 : 0;
   plan->grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   return THMR_OK;
 }

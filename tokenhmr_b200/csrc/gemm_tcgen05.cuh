@@ -70,25 +70,28 @@ struct GemmParams {
   unsigned int* sk_flags;
   int sk_tiles;   // trailing tiles scheduled stream-K (gemm2_tcgen05.cuh G2Work)
   unsigned long long* stamp;   // in-graph start stamp (common.cuh stamp_start), nullable
+  int m_fast;     // 1-CTA kernel: row tile fastest in the tile order (see TileIter)
   int l2_hints;   // CTA-pair kernel: bit 0 = A operand loaded evict_first (dead after this GEMM), bit 2 = reduce-add evict_last
   unsigned long long* dbg_counters;  // optional [gridDim.x][8] cycle counters (scripts/dev_gemm_qkv.py)
   int dbg;                 // THMR_GEMM_DBG experiments: 1 = skip epilogue work, 2 = skip only the TMA store
 };
 
 // Tile order shared by the three warp roles.  Normal mode: tiles round-robin over CTAs, column tile
-// fastest.  Row-argmin mode: row blocks round-robin over CTAs, all column tiles of a row block in sequence.
+// fastest -- or row tile fastest (GemmParams::m_fast, chosen by the host when M < N): the CTAs of a wave then share the
+// tiles of the LARGER operand, which is streamed from HBM once instead of once per wave (SMPL blend GEMM: 512 poses x
+// 20672 basis rows).  Row-argmin mode: row blocks round-robin over CTAs, all column tiles of a row block in sequence.
 struct TileIter {
   int tiles_m, tiles_n, m_blk, n_blk, tile, num_tiles;
-  bool m_stationary;
-  __device__ TileIter(int tm, int tn, bool ms) : tiles_m(tm), tiles_n(tn), m_stationary(ms) {
+  bool m_stationary, m_fast;
+  __device__ TileIter(int tm, int tn, bool ms, bool mf = false) : tiles_m(tm), tiles_n(tn), m_stationary(ms), m_fast(mf) {
     num_tiles = tm * tn;
     tile = blockIdx.x;
     m_blk = blockIdx.x;
     n_blk = 0;
   }
   __device__ bool valid() const { return m_stationary ? (m_blk < tiles_m) : (tile < num_tiles); }
-  __device__ int m0(int bm) const { return (m_stationary ? m_blk : tile / tiles_n) * bm; }
-  __device__ int n0(int bn) const { return (m_stationary ? n_blk : tile % tiles_n) * bn; }
+  __device__ int m0(int bm) const { return (m_stationary ? m_blk : (m_fast ? tile % tiles_m : tile / tiles_n)) * bm; }
+  __device__ int n0(int bn) const { return (m_stationary ? n_blk : (m_fast ? tile / tiles_m : tile % tiles_n)) * bn; }
   __device__ bool last_n() const { return n_blk == tiles_n - 1; }
   __device__ void next() {
     if (m_stationary) {
@@ -249,7 +252,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr, p.m_fast != 0); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -288,7 +291,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // The readiness of the NEXT smem stage is probed right after the MMA issues of the current one, so the latency of
       // mbarrier.try_wait (~100-200 cycles even when the phase is complete) overlaps with tensor work.
       bool ready = false;
-      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr, p.m_fast != 0); it.valid(); it.next()) {
         long long t0 = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         w_tempty += clock64() - t0;
@@ -346,7 +349,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float second = INFINITY;                 // screened arg-min: second-smallest value of the row
       const bool screen = p.argmin_out != nullptr && p.screen_rows != nullptr;
       const float m2a = -2.0f * p.alpha;
-      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr); it.valid(); it.next()) {
+      for (TileIter it(tiles_m, tiles_n, p.argmin_out != nullptr, p.m_fast != 0); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
         const int row = m0 + q * 32 + lane;
@@ -389,19 +392,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float c2[4];
                 c2[0] = __shfl_sync(0xffffffffu, cq.x, bl); c2[1] = __shfl_sync(0xffffffffu, cq.y, bl);
                 c2[2] = __shfl_sync(0xffffffffu, cq.z, bl); c2[3] = __shfl_sync(0xffffffffu, cq.w, bl);
-                float d[4];
+                // (a group-minimum pre-test that skips columns above the current second best was tried: the divergent branch
+                //  cost more than the skipped min / compare / select chain saved, 2.17 vs 1.95 ms per 1 M queries)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) d[e] = fmaf(m2a, __uint_as_float(v[j + e]), c2[e]);
-                // only values below the current second best can change (best, second): after the first few hundred columns
-                // that is rare, so four columns are screened with one group minimum (the min / compare / select chain of the
-                // full update made this epilogue ALU-pipe bound: 9.4 instructions per element, tensor pipe 26 %)
-                if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < second) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    second = fminf(second, fmaxf(d[e], best));
-                    if (d[e] < best) best_idx = col0 + j + e;
-                    best = fminf(best, d[e]);
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const float d = fmaf(m2a, __uint_as_float(v[j + e]), c2[e]);
+                  second = fminf(second, fmaxf(d, best));
+                  if (d < best) best_idx = col0 + j + e;
+                  best = fminf(best, d);
                 }
               }
             }
@@ -553,7 +551,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int sw = lane & 7;
       long long w_tfull = 0, w_store = 0, w_ldtm = 0, w_alu = 0, w_sts = 0, w_fence = 0;
       const long long t_begin = clock64();
-      for (TileIter it(tiles_m, tiles_n, false); it.valid(); it.next()) {
+      for (TileIter it(tiles_m, tiles_n, false, p.m_fast != 0); it.valid(); it.next()) {
         const int m0 = it.m0(kGemmBM);
         const int n0 = it.n0(BN);
         // this warp's BN/2 bias values (lane l: columns 4l..4l+3 of its column half), fetched while the MMAs run
