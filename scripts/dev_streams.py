@@ -72,10 +72,12 @@ out["resident plain engine 1 stream"] = resident(plain, 1)
 out["e2e plain engine depth2 streams1"] = e2e(plain, 2, 1)
 del plain
 torch.cuda.empty_cache()
-conc = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, concurrent=True, max_cached_shapes=8)
-for n in (1, 2, 3, 4):
+conc = TokenHMREngine(cfg, sd, smpl, device=dev, use_cuda_graph=True, concurrent=True, max_cached_shapes=16)
+for n in [int(a) for a in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,2,3,4".split(","))]:
     out[f"resident concurrent engine {n} streams"] = resident(conc, n)
-for depth, streams in ((2, 2), (3, 2), (4, 2), (3, 3), (6, 3), (4, 4)):
+combos = [tuple(int(v) for v in c.split("x")) for c in (sys.argv[3].split(",") if len(sys.argv) > 3 else
+                                                          "2x2,3x2,4x2,3x3,6x3,4x4".split(","))]
+for depth, streams in combos:
     out[f"e2e concurrent engine depth{depth} streams{streams}"] = e2e(conc, depth, streams)
 for k, v in out.items():
     print(f"{k:48s} {v:7.3f} ms/step  {B * 1e3 / v:7.0f} images/s")

@@ -1,0 +1,73 @@
+"""Second session of round 2: turn the scratch outputs of scripts/r2{b,c,d,e,f}_gpu_run.sh (gpurun_out/) into tracked
+artefacts under profiles/ (prefix r2b_)."""
+import json, re, shutil, subprocess
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+P, G = ROOT / "profiles", ROOT / "gpurun_out"
+
+txt = subprocess.run(["python", str(ROOT / "scripts/ncu_summarize.py"), str(G / "r2b_prof_vq.ncu-rep"), str(G / "r2d_prof_lbs.ncu-rep")],
+                     capture_output=True, text=True).stdout
+hdr = """# r2b ncu --set full captures (--clock-control none; ncu flushes the caches before every replay: DRAM bytes and times are cold-cache
+# figures), second session of round 2.
+# r2b_prof_vq: thmr_vq_argmin, 1 M x 2048 x 256, screened schedule (csrc/vq.cuh): launches 7 and 8 of gemm_f16_tn_kernel<256,4,Generic>
+#   = pass 1 (one fp16 product per pair, best + second best in the epilogue) over a full 131072-row chunk and over the last, 82496-row
+#   chunk; launch 9 = the exact 3-product pass over the ~110 k queued rows (row count read from device memory).
+# r2d_prof_lbs: thmr_lbs, 4096 poses: the SMPL blend GEMM of one 512-pose chunk (gemm_f16_tn_kernel<256,4,Store32>, row-fastest tile
+#   order) and the skinning kernel smpl_skin_kernel<256,4> (40 registers, 864 blocks = one wave); under ncu the skinning kernel
+#   reads its 43 MB of blended vertices from DRAM (flushed), inside thmr_lbs they are L2 hits.
+
+"""
+(P / "r2b_ncu_summary.md").write_text(hdr + txt)
+
+def launch_table(src, dst_csv, dst_md, title):
+    shutil.copy(G / src, P / dst_csv)
+    out = subprocess.run(["python", str(ROOT / "scripts/launch_summary.py"), str(G / src)], capture_output=True, text=True).stdout
+    (P / dst_md).write_text(title + "\n\n" + out)
+
+launch_table("r2b_vq_launches.csv", "r2b_vq_launches.csv", "r2b_vq_launches_summary.md",
+             "# r2b launch list of scripts/dev_vq_lbs.py vq (ncu --metrics gpu__time_duration.sum --clock-control none, first 90 launches:\n"
+             "# ~3.3 calls of thmr_vq_argmin on 1 M queries, screened schedule).  Per call: 1 codebook split, 1 prep, 8 x (fp16 cast of a\n"
+             "# 131072-row chunk 33 us + pass-1 GEMM 173 us), 4 x (gather+split, exact GEMM: 54 + 320 us for the first round, ~7 us for the\n"
+             "# three rounds that find no rows).  Cold-cache, serialised per-launch times.")
+launch_table("r2c_lbs_launches.csv", "r2b_lbs_launches.csv", "r2b_lbs_launches_summary.md",
+             "# r2b launch list of scripts/dev_vq_lbs.py lbs (thmr_lbs, 4096 poses, pose2rot): per call 1 pose kernel (27 us), 8 x (blend GEMM\n"
+             "# 28 us + skinning 33 us).  Cold-cache, serialised per-launch times (ncu).")
+
+blocks = txt.split("- Kernel Name:")[1:]
+def val(b, key):
+    m = re.search(re.escape(key) + r": ([0-9.]+) (\S*)", b)
+    if not m: return None
+    v, u = float(m.group(1)), m.group(2)
+    return v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(u, 1) if "byte" in u else v
+p1, ex = blocks[0], blocks[2]
+(P / "r2b_vq_traffic.json").write_text(json.dumps({
+    "schedule": "screened (csrc/vq.cuh): fp16 cast -> 1-product pass with best / second best -> exact 3-product pass on the queued rows",
+    "pass1_chunk_131072_rows": {"us": val(p1, "gpu__time_duration.sum"), "dram_read": int(val(p1, "dram__bytes_read.sum")),
+                                "dram_write": int(val(p1, "dram__bytes_write.sum")),
+                                "tensor_pipe_pct": val(p1, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")},
+    "exact_pass_about_110k_rows": {"us": val(ex, "gpu__time_duration.sum"), "dram_read": int(val(ex, "dram__bytes_read.sum")),
+                                   "dram_write": int(val(ex, "dram__bytes_write.sum")),
+                                   "tensor_pipe_pct": val(ex, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")},
+    "per_1M_queries_in_situ_estimate": {"dram_read": int(1.11 * 1.024e9 + val(ex, "dram__bytes_read.sum")), "algorithmic_bytes": 1034000000,
+                                        "how": "fp32 queries once (cast) + ~11 % again (gather for the exact pass) + the exact pass's operand; "
+                                               "the pass-1 operand is L2-resident between the cast and the GEMM"},
+    "note": "cold-cache ncu figures.  The fp16 operand of a pass-1 chunk (67 MB) is written by the cast kernel right before the GEMM and is an L2 "
+            "hit inside thmr_vq_argmin (ncu flushes it: the 68.8 MB read above); per 1 M queries the schedule reads the 1.02 GB of fp32 queries "
+            "once for the cast and ~11 % of them again for the exact pass, instead of writing and re-reading a 1.5 GB split operand "
+            "(profiles/r2_vq_traffic.json: 1.54 GB read by the GEMM alone)"}, indent=1))
+
+for src, dst in (("r2d_bench_b200_n1.json", "r2b_bench_b200_n1.json"), ("r2f_bench_b200_n2.json", "r2b_bench_b200_n2.json")):
+    line = open(G / src).read().strip().splitlines()[-1]
+    json.loads(line)
+    (P / dst).write_text(line + "\n")
+
+def table(log):
+    rows = [l.rstrip() for l in open(G / log) if "ms/step" in l]
+    return "\n".join("    " + r for r in rows)
+(P / "r2b_streams.md").write_text(
+    "# Steps in flight: device-resident replay on n streams and the end-to-end pipeline at (depth, streams) settings\n"
+    "# (scripts/dev_streams.py, bs=64 release forward, best of 3 runs of 24 steps; 'plain' = default engine with the stream-K fc2,\n"
+    "# 'concurrent' = TokenHMREngine(concurrent=True): whole-tile fc2, safe next to other kernels).  Two different boxes of the pool.\n\n"
+    "## box A (gpurun_out/r2c_streams.log)\n\n" + table("r2c_streams.log") + "\n\n## box B (gpurun_out/r2e_streams.log)\n\n" + table("r2e_streams.log") + "\n")
+d = json.loads((P / "r2b_bench_b200_n1.json").read_text())
+print("bench", d["ms_per_step"], d["value"], d["e2e"]["value"], d["streams_1"]["value"], d["roofline"]["frac"])
