@@ -212,6 +212,23 @@ def test_two_stream_pipeline_matches_synchronous_forward(cuda_dev):
         TokenHMRPipeline(model, depth=2, streams=3)
 
 
+def test_concurrent_engine_matches_default_engine_at_bs64(cuda_dev, tiny):
+    """thmr_config::concurrent only swaps the stream-K fc2 schedule (which at bs=64 cuts 92 of the 240 output tiles into
+    partial sums) for whole tiles: same products, different fp32 summation order -> outputs agree to rounding, and both
+    engines launch the same number of kernels."""
+    from tokenhmr_b200 import synth
+    from tokenhmr_b200.engine import TokenHMREngine
+    cfg, sd, smpl, model = tiny
+    conc = TokenHMREngine(cfg, sd, smpl, device=cuda_dev, use_cuda_graph=False, concurrent=True)
+    img = synth.make_images(64, cfg, seed=77).to(cuda_dev)
+    a, b = model({"img": img}, return_taps=True), conc({"img": img}, return_taps=True)
+    for k in ("_vit_tokens", "pred_vertices", "pred_keypoints_3d", "pred_cam", "cls_logits_softmax"):
+        assert rel_err(b[k], a[k]) < 2e-4, (k, rel_err(b[k], a[k]))
+    same = (a["cls_logits_softmax"].argmax(-1) == b["cls_logits_softmax"].argmax(-1)).float().mean().item()
+    assert same > 0.995, same
+    assert model.num_launches() == conc.num_launches()
+
+
 def test_release_forward_vs_reference_golden(cuda_dev, golden_dir):
     """Full ViT-H/16 depth-32 forward (B=2) against the outputs of the LIVE reference modules (fp32)."""
     from tokenhmr_b200 import synth

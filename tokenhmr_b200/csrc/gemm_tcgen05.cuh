@@ -385,7 +385,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (screen) {
             // pass 1 of the screened arg-min: e = col_sq - 2 alpha acc (the row norm is common to every column), running
             // best / second best; ties and near-ties are settled by the exact pass, so only the margin matters here
+            // The epilogue is ALU-pipe bound (min / compare / select are half rate), so the column index rides in the value: the
+            // low byte of e's mantissa is replaced by the column's position in its 32-column chunk (one byte permute), which
+            // perturbs e by < 2^-15 relative (covered by screen_abs), and the chunk itself is noted once per chunk.  Three
+            // min / max and a permute per column instead of three min / max, a compare, a select and the index arithmetic.
             if (col0 < p.N) {   // (warp-uniform: shuffles below need every lane; N % 32 == 0 is checked by the host)
+              const float best_before = best;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int bl = (cc * 32 + j) >> 2;
@@ -397,11 +402,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float d = fmaf(m2a, __uint_as_float(v[j + e]), c2[e]);
-                  second = fminf(second, fmaxf(d, best));
-                  if (d < best) best_idx = col0 + j + e;
-                  best = fminf(best, d);
+                  // low byte of the value := position in the chunk (one PRMT; the byte constants live in 8 registers)
+                  const float k = __uint_as_float(__byte_perm(__float_as_uint(d), 0x03020100u + 0x04040404u * ((j + e) >> 2),
+                                                              0x3214u + ((j + e) & 3)));
+                  second = fminf(second, fmaxf(k, best));
+                  best = fminf(best, k);
                 }
               }
+              if (best < best_before) best_idx = col0;   // chunk of the running best; the column is in the key's low bits
             }
           } else if (p.argmin_out) {
             if (col0 < p.N) {   // (warp-uniform: shuffles below need every lane)
@@ -502,6 +510,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (p.argmin_out && it.last_n()) {
           // merge the two column halves: smaller distance wins, equal distances -> smaller index
           // (== first minimum over the whole row, as torch.min returns)
+          if (screen) best_idx += static_cast<int>(__float_as_uint(best) & 255u);   // unpack the column (pass-1 keys)
           if (half == 1) {
             xch_val[q * 32 + lane] = best; xch_idx[q * 32 + lane] = best_idx; xch_sec[q * 32 + lane] = second;
           }

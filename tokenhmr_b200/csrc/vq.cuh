@@ -59,7 +59,9 @@ vq_split_rows_kernel(const float* __restrict__ x, __half* __restrict__ out, floa
 // none when queries sit near a code) are queued and re-done by the exact pass, which also owns the first-minimum tie rule.
 // Results are therefore identical to running the exact pass on every row.
 constexpr float kVqScreenRel = 0.00390625f * 1.05f;   // 2 eps / (|x| cmax) = 2^-8, 5 % head-room
-constexpr float kVqScreenAbs = 1.0e-5f;               // fp32 rounding of (x^2 - 2 x.c) + c^2 and of the accumulation
+constexpr float kVqScreenAbs = 1.4e-4f;               // fp32 rounding of (x^2 - 2 x.c) + c^2 and of the accumulation (1e-5) + the column
+                                                      // index packed into the low mantissa BYTE of pass 1's values: two keys,
+                                                      // each off by < 2^-15 |e|, |e| <= 2 (|x|^2 + max|c|^2)  (1.23e-4)
 constexpr int kVqScreenChunk = 131072;                // pass-1 rows per launch: 64 MB of fp16 operand stays in the L2
 constexpr int kVqExactCap = 262144;                   // rows per exact-pass round (bounds the split-operand scratch)
 
