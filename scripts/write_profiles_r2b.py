@@ -5,13 +5,15 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 P, G = ROOT / "profiles", ROOT / "gpurun_out"
 
-txt = subprocess.run(["python", str(ROOT / "scripts/ncu_summarize.py"), str(G / "r2b_prof_vq.ncu-rep"), str(G / "r2d_prof_lbs.ncu-rep")],
+txt = subprocess.run(["python", str(ROOT / "scripts/ncu_summarize.py"), str(G / "r2h_prof_vq.ncu-rep"), str(G / "r2d_prof_lbs.ncu-rep")],
                      capture_output=True, text=True).stdout
 hdr = """# r2b ncu --set full captures (--clock-control none; ncu flushes the caches before every replay: DRAM bytes and times are cold-cache
 # figures), second session of round 2.
-# r2b_prof_vq: thmr_vq_argmin, 1 M x 2048 x 256, screened schedule (csrc/vq.cuh): launches 7 and 8 of gemm_f16_tn_kernel<256,4,Generic>
-#   = pass 1 (one fp16 product per pair, best + second best in the epilogue) over a full 131072-row chunk and over the last, 82496-row
-#   chunk; launch 9 = the exact 3-product pass over the ~110 k queued rows (row count read from device memory).
+# r2h_prof_vq: thmr_vq_argmin, 1 M x 2048 x 256, screened schedule (csrc/vq.cuh), final kernel (column packed into the value's low
+#   byte): launches 7 and 8 of gemm_f16_tn_kernel<256,4,Generic> = pass 1 (one fp16 product per pair, best + second best in the
+#   epilogue) over a full 131072-row chunk and over the last, 82496-row chunk; launch 9 = the exact 3-product pass over the ~120 k
+#   queued rows (row count read from device memory).  Before the packing (compare / select / index add per column) the full chunk
+#   took 173.6 us at 42 % tensor pipe (gpurun_out/r2b_prof_vq.ncu-rep).
 # r2d_prof_lbs: thmr_lbs, 4096 poses: the SMPL blend GEMM of one 512-pose chunk (gemm_f16_tn_kernel<256,4,Store32>, row-fastest tile
 #   order) and the skinning kernel smpl_skin_kernel<256,4> (40 registers, 864 blocks = one wave); under ncu the skinning kernel
 #   reads its 43 MB of blended vertices from DRAM (flushed), inside thmr_lbs they are L2 hits.
@@ -24,10 +26,10 @@ def launch_table(src, dst_csv, dst_md, title):
     out = subprocess.run(["python", str(ROOT / "scripts/launch_summary.py"), str(G / src)], capture_output=True, text=True).stdout
     (P / dst_md).write_text(title + "\n\n" + out)
 
-launch_table("r2b_vq_launches.csv", "r2b_vq_launches.csv", "r2b_vq_launches_summary.md",
+launch_table("r2h_vq_launches.csv", "r2b_vq_launches.csv", "r2b_vq_launches_summary.md",
              "# r2b launch list of scripts/dev_vq_lbs.py vq (ncu --metrics gpu__time_duration.sum --clock-control none, first 90 launches:\n"
              "# ~3.3 calls of thmr_vq_argmin on 1 M queries, screened schedule).  Per call: 1 codebook split, 1 prep, 8 x (fp16 cast of a\n"
-             "# 131072-row chunk 33 us + pass-1 GEMM 173 us), 4 x (gather+split, exact GEMM: 54 + 320 us for the first round, ~7 us for the\n"
+             "# 131072-row chunk 33 us + pass-1 GEMM), 4 x (gather+split, exact GEMM: the first round does the work, ~7 us for the\n"
              "# three rounds that find no rows).  Cold-cache, serialised per-launch times.")
 launch_table("r2c_lbs_launches.csv", "r2b_lbs_launches.csv", "r2b_lbs_launches_summary.md",
              "# r2b launch list of scripts/dev_vq_lbs.py lbs (thmr_lbs, 4096 poses, pose2rot): per call 1 pose kernel (27 us), 8 x (blend GEMM\n"
@@ -56,7 +58,8 @@ p1, ex = blocks[0], blocks[2]
             "once for the cast and ~11 % of them again for the exact pass, instead of writing and re-reading a 1.5 GB split operand "
             "(profiles/r2_vq_traffic.json: 1.54 GB read by the GEMM alone)"}, indent=1))
 
-for src, dst in (("r2d_bench_b200_n1.json", "r2b_bench_b200_n1.json"), ("r2f_bench_b200_n2.json", "r2b_bench_b200_n2.json")):
+for src, dst in (("r2g_bench_b200_n1.json", "r2b_bench_b200_n1.json"), ("r2d_bench_b200_n1.json", "r2b_bench_b200_n1_faster_box.json"),
+                 ("r2f_bench_b200_n2.json", "r2b_bench_b200_n2.json")):
     line = open(G / src).read().strip().splitlines()[-1]
     json.loads(line)
     (P / dst).write_text(line + "\n")
