@@ -85,3 +85,20 @@ def test_product_never_imports_the_oracle():
     for f in (ROOT / "tokenhmr_b200").rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_vq_workspace_covers_both_schedules(built_lib):
+    """thmr_vq_workspace_bytes is pure arithmetic (no CUDA call): it covers BOTH schedules of thmr_vq_argmin (the single exact
+    pass needs a Q x 3D fp16 split operand; the screened one a 131072-row fp16 chunk, a 262144-row exact-pass round and the row
+    queue), so that switching THMR_VQ_SCREEN never invalidates a caller's buffer, and it never shrinks when Q grows."""
+    K, D = 2048, 256
+    small = built_lib.thmr_vq_workspace_bytes(960, K, D)
+    assert small >= 960 * 3 * D * 2 + K * 3 * D * 2
+    prev = 0
+    for Q in (960, 8192, 40960, 262144, 1_000_000, 4_000_000):
+        n = built_lib.thmr_vq_workspace_bytes(Q, K, D)
+        assert n >= prev and n % 1024 == 0
+        prev = n
+    assert built_lib.thmr_vq_workspace_bytes(1_000_000, K, D) >= 1_000_000 * 3 * D * 2 + 1_000_000 * 4     # exact layout covered
+    assert built_lib.thmr_vq_workspace_bytes(1_000_000, K, D) >= 131072 * D * 2 + 262144 * 3 * D * 2 + 1_000_000 * 8  # screened
+    assert built_lib.thmr_abi_version() >= 5          # thmr_config::concurrent
