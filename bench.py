@@ -579,7 +579,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step_head, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": dict(workload_config(world), streams=head["streams"]),
+            "config": workload_config(world),           # identical for both arms (the driver compares them)
+            "steps_in_flight": head["streams"],         # streams the K timed steps were replayed on (see streams_1 / streams_n)
             "streams_1": serial, "streams_n": dual,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "read_back": consumed, "streams": e2e_streams, "modes": e2e_modes,
