@@ -581,6 +581,10 @@ def main():
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": workload_config(world),           # identical for both arms (the driver compares them)
             "steps_in_flight": head["streams"],         # streams the K timed steps were replayed on (see streams_1 / streams_n)
+            "scaling_note": (None if world == 1 else
+                             "every rank keeps ONE step in flight (the sharded forward carries its NCCL all-gather inside the CUDA "
+                             "graph; the multi-stream mode is single-GPU only): the like-for-like single-GPU number is `streams_1` "
+                             "of the N=1 line, not its `value` when that was measured with several steps in flight"),
             "streams_1": serial, "streams_n": dual,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "read_back": consumed, "streams": e2e_streams, "modes": e2e_modes,
