@@ -226,6 +226,26 @@ def rodrigues_goldens(ns) -> None:
     print("wrote rodrigues golden")
 
 
+def vq_large_golden(ns) -> None:
+    """QuantizeEMAReset.quantize (quantize_cnn.py:80-86) from the LIVE reference class on 65536 unstructured queries: large
+    enough for the screened two-pass schedule of thmr_vq_argmin (Q >= 8192, several exact-pass row blocks), so that the
+    library's default path is compared with the reference itself and not only with its own exact pass.  The whole distance
+    matrix (512 MB) is formed at once, exactly as the reference does."""
+    cfg = release_config()
+    qz = ns.quantize_cnn.QuantizeEMAReset(cfg.nb_code, cfg.code_dim)
+    codebook = torch.randn(cfg.nb_code, cfg.code_dim, generator=torch.Generator().manual_seed(1))
+    qz.codebook = codebook
+    x = torch.randn(65536, cfg.code_dim, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        idx = qz.quantize(x)
+        k_w = codebook.t()
+        d = (x ** 2).sum(-1, keepdim=True) - 2 * x @ k_w + (k_w ** 2).sum(0, keepdim=True)
+        top2 = d.topk(2, dim=-1, largest=False).values
+    np.savez_compressed(GOLDEN / "vq_quantize_64k.npz", idx=idx.numpy().astype(np.int16),
+                        gap=(top2[:, 1] - top2[:, 0]).numpy().astype(np.float32))
+    print("wrote vq_quantize_64k.npz")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--release", action="store_true")
@@ -245,6 +265,9 @@ def main() -> None:
     if args.only == "encoder":
         encoder_goldens(ref_import.load_modules())
         return
+    if args.only == "vq":
+        vq_large_golden(ref_import.load_modules())
+        return
     if args.only == "forward":
         ns = ref_import.load_modules()
         forward_golden(ns, tiny_config(vit_depth=2), 2, "forward_tiny_d2.npz")
@@ -254,6 +277,7 @@ def main() -> None:
         return
     ns = ref_import.load_modules()
     stage_goldens(ns)
+    vq_large_golden(ns)
     eval_goldens()
     preproc_goldens()
     encoder_goldens(ns)

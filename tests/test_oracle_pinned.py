@@ -42,6 +42,17 @@ def test_forward_release_matches_reference_golden(golden_dir):
     _check_forward(golden_dir / "forward_release_d32.npz", release_config(), 2)
 
 
+def test_vq_quantize_64k_matches_reference_golden(golden_dir):
+    """65536 queries (the size class that takes the library's screened two-pass schedule): the restatement equals the LIVE
+    reference's QuantizeEMAReset.quantize on every row."""
+    g = np.load(golden_dir / "vq_quantize_64k.npz")
+    cb = torch.randn(2048, 256, generator=torch.Generator().manual_seed(1))
+    x = torch.randn(65536, 256, generator=torch.Generator().manual_seed(12))
+    assert np.array_equal(O.vq_quantize(x, cb).numpy(), g["idx"].astype(np.int64))
+    gap = O.vq_top2_gap(x, cb).numpy()
+    assert np.allclose(gap, g["gap"], rtol=0, atol=1e-4)
+
+
 def test_vq_quantize_matches_reference_golden(golden_dir):
     g = np.load(golden_dir / "vq_quantize.npz")
     cb = torch.randn(2048, 256, generator=torch.Generator().manual_seed(1))
